@@ -1,0 +1,180 @@
+/* dis_c.h -- C-ABI of libdis_b200.so, the B200-native Dense Inverse Search optical-flow engine.
+ *
+ * This is the drop-in boundary for the reference's hot path (zhaorz/FlowOnTheGo, CPU tree
+ * `kroeger/`): frame pair in -> dense flow out.  Every entry point names the reference
+ * interface it replaces.  Plain pointers and sizes only; every function returns a dis_status
+ * (0 = ok) unless stated otherwise.  There is no CPU fallback: without a CUDA device (or with a
+ * device that is not sm_100) dis_create fails with DIS_ERR_CUDA / DIS_ERR_UNSUPPORTED.
+ *
+ * Scope: SELECTMODE=1 (optical flow), SELECTCHANNEL=1 (grey) -- the reference's `run_OF_INT`
+ * binary (kroeger/CMakeLists.txt:44-48).
+ */
+#ifndef DIS_C_H
+#define DIS_C_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum dis_status {
+  DIS_OK = 0,
+  DIS_ERR_INVALID_ARG = 1, /* null pointer, non-positive size, size larger than the handle was created for */
+  DIS_ERR_UNSUPPORTED = 2, /* parameter combination outside the scoped mode (see dis_params) */
+  DIS_ERR_CUDA = 3,        /* CUDA runtime error; text in dis_last_error() */
+  DIS_ERR_IO = 4,          /* file could not be read / written / parsed */
+  DIS_ERR_NOMEM = 5
+} dis_status;
+
+/* The 20 explicit command-line parameters of the reference, in CLI order
+ * (kroeger/run_dense.cpp:271-291, kroeger/README.md:71-88).  Meaning and defaults are the
+ * reference's (kroeger/oflow.h:31-76). */
+typedef struct dis_params {
+  int32_t lv_f;        /*  1 coarsest scale (sc_f)                                   */
+  int32_t lv_l;        /*  2 finest scale (sc_l)                                     */
+  int32_t maxiter;     /*  3 max. Gauss-Newton iterations per patch and scale        */
+  int32_t miniter;     /*  4 min. iterations                                         */
+  float mindprate;     /*  5 dp_thresh  (squared internally, oflow.cpp:88)           */
+  float mindrrate;     /*  6 dr_thresh                                               */
+  float minimgerr;     /*  7 res_thresh                                              */
+  int32_t patchsz;     /*  8 patch edge length p (even, 4..16)                       */
+  float poverl;        /*  9 patch overlap in [0,1): steps = max(1, floor(p*(1-ov))) */
+  int32_t usefbcon;    /* 10 forward-backward consistency merge                      */
+  int32_t patnorm;     /* 11 mean-normalise patches                                  */
+  int32_t costfct;     /* 12 0 = L2, 1 = L1, 2 = pseudo-Huber                        */
+  int32_t usetvref;    /* 13 variational refinement on/off                           */
+  float tv_alpha;      /* 14 */
+  float tv_gamma;      /* 15 */
+  float tv_delta;      /* 16 */
+  int32_t tv_innerit;  /* 17 inner fixed-point iterations = tv_innerit*(level+1)     */
+  int32_t tv_solverit; /* 18 SOR sweeps per inner iteration                          */
+  float tv_sor;        /* 19 SOR omega                                               */
+  int32_t verbosity;   /* 20 0 silent, 1 total run time line, 2 per-scale TIME lines */
+} dis_params;
+
+/* Device-side stage timings of the last run (CUDA events), the counterpart of the reference's
+ * gettimeofday brackets (kroeger/oflow.cpp:112-128, 199-304, 354-360). Milliseconds. */
+typedef struct dis_timings {
+  float total_ms;   /* whole run incl. copies when host buffers are used */
+  float h2d_ms;     /* host -> device copy of the inputs                  */
+  float pyramid_ms; /* stage 1: pyramid + gradients (0 for dis_run_pyramids) */
+  float search_ms;  /* stage 2: template/Hessian + coarse init + inverse search, all scales */
+  float densify_ms; /* stage 3: densification, all scales */
+  float varref_ms;  /* stage 4: variational refinement, all scales */
+  float finish_ms;  /* upsample + crop */
+  float d2h_ms;     /* device -> host copy of the result */
+  int32_t launches; /* kernels launched by the last run */
+} dis_timings;
+
+typedef struct dis_handle dis_handle;
+
+/* ---- parameter helpers (host only, no CUDA) -------------------------------------------- */
+
+/* kroeger/run_dense.cpp:180-183 AutoFirstScaleSelect */
+int dis_auto_first_scale(int imgwidth, int fratio, int patchsize);
+
+/* Operating points 1..4 of kroeger/run_dense.cpp:225-267 for an image of width `width_org`
+ * (anything else selects 2, like the reference's `default:` label).  verbosity is set to 2. */
+int dis_params_preset(dis_params* out, int preset, int width_org);
+
+/* The 20 explicit parameters as strings in CLI order (argv[4..23] of the reference,
+ * kroeger/run_dense.cpp:271-291; parsed with atoi/atof like the reference). */
+int dis_params_from_argv(dis_params* out, int n, const char* const* args);
+
+/* Checks a parameter set against the scoped mode; on failure writes a reason into `why`. */
+int dis_params_validate(const dis_params* p, char* why, size_t why_len);
+
+/* Padded size the reference would work on: multiple of 2^lv_f (kroeger/run_dense.cpp:298-311). */
+int dis_padded_size(int w, int h, int lv_f, int* w_pad, int* h_pad, int* left, int* top);
+
+/* ---- engine lifetime ------------------------------------------------------------------- */
+
+/* Creates an engine on CUDA device `device` with workspace for images up to max_w x max_h
+ * (unpadded input size).  One handle owns one CUDA stream; several handles run concurrently. */
+int dis_create(const dis_params* params, int max_w, int max_h, int device, dis_handle** out);
+int dis_destroy(dis_handle* h);
+/* Replaces the parameter set (workspace is re-planned; fails if it no longer fits). */
+int dis_set_params(dis_handle* h, const dis_params* params);
+/* Last error text of this handle (or of dis_create when h is NULL). Never NULL. */
+const char* dis_last_error(const dis_handle* h);
+
+/* ---- the reference's engine boundary --------------------------------------------------- */
+
+/* Replaces `OFC::OFClass::OFClass(...)` (kroeger/oflow.h:84-111, oflow.cpp:32-363; called at
+ * kroeger/run_dense.cpp:391-400).  Same argument meaning: six host pyramids indexed by level
+ * [0..lv_f] (entries below lv_l may be NULL; the gradient pyramids of image b are only read
+ * when usefbcon is set), each a row-major float image of (width/2^l + 2*imgpadding) x
+ * (height/2^l + 2*imgpadding); width/height are the padded sizes (multiples of 2^lv_f);
+ * outflow receives (width/2^lv_l) x (height/2^lv_l) interleaved (u,v); initflow is optional
+ * (resolution of level lv_f+1).  imgpadding must equal params.patchsz as in the reference's
+ * only caller.  Synchronous. */
+int dis_run_pyramids(dis_handle* h, const float* const* im_ao, const float* const* im_ao_dx,
+                     const float* const* im_ao_dy, const float* const* im_bo,
+                     const float* const* im_bo_dx, const float* const* im_bo_dy, int imgpadding,
+                     int width, int height, const float* initflow, float* outflow);
+
+/* ---- the whole `run_dense` data path --------------------------------------------------- */
+
+/* Replaces kroeger/run_dense.cpp:298-414 between imread and SaveFlowFile: divisibility padding,
+ * u8->f32, pyramid + gradients (ConstructImgPyramide :130-178) -- all on the GPU -- then the
+ * engine, then x2^lv_l upsampling and cropping.  a,b: host, row pitch in bytes, w x h grey u8.
+ * flow_out: host, w*h*2 floats, interleaved (u,v), full resolution.  Synchronous. */
+int dis_run_u8(dis_handle* h, const uint8_t* a, const uint8_t* b, int w, int h_img, int pitch,
+               float* flow_out);
+
+/* Asynchronous variant: enqueues copy-in, compute and copy-out on the handle's stream and
+ * returns.  Buffers must stay valid (and should be pinned, see dis_host_alloc) until
+ * dis_wait().  At most one submission may be in flight per handle. */
+int dis_submit_u8(dis_handle* h, const uint8_t* a, const uint8_t* b, int w, int h_img, int pitch,
+                  float* flow_out);
+int dis_wait(dis_handle* h);
+
+/* Device-resident variant for batched streams: d_a, d_b and d_flow are device pointers on the
+ * handle's device; work is enqueued on the handle's stream (asynchronous; use dis_wait). */
+int dis_submit_u8_device(dis_handle* h, const uint8_t* d_a, const uint8_t* d_b, int w, int h_img,
+                         int pitch, float* d_flow);
+
+/* Raw engine output of the last run_u8 (level lv_l, padded size), for parity tests against the
+ * reference's OFClass output before the OpenCV upsampling: (w_pad/2^lv_l)*(h_pad/2^lv_l)*2. */
+int dis_fetch_level_flow(dis_handle* h, float* out, size_t n_floats);
+
+/* CUDA stream of the handle as a cudaStream_t (void* here to keep CUDA out of the header). */
+void* dis_stream(dis_handle* h);
+int dis_get_timings(dis_handle* h, dis_timings* out);
+/* Enables per-stage event timing (off by default; stage timers add synchronisation points). */
+int dis_enable_stage_timing(dis_handle* h, int on);
+
+/* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost). */
+int dis_host_alloc(void** ptr, size_t bytes);
+int dis_host_free(void* ptr);
+
+/* ---- .flo I/O (kroeger/run_dense.cpp:16-57 SaveFlowFile; flow_code/C/flowIO.cpp:46-133) -- */
+int dis_write_flo(const char* path, const float* flow_uv, int w, int h);
+/* Reads the header into *w,*h; if flow_uv is non-NULL (capacity n_floats) also the data. */
+int dis_read_flo(const char* path, float* flow_uv, size_t n_floats, int* w, int* h);
+
+/* ---- stage-level debug taps (tests only; never on the timed path) ---------------------- */
+typedef enum dis_tap {
+  DIS_TAP_IMG_A = 0,   /* padded pyramid image a, level l: (w_l+2p) x (h_l+2p)         */
+  DIS_TAP_IMG_A_DX = 1,
+  DIS_TAP_IMG_A_DY = 2,
+  DIS_TAP_IMG_B = 3,
+  DIS_TAP_PATCH_FLOW = 4,   /* per patch (u,v) after the inverse search, patch index x*noph+y */
+  DIS_TAP_FLOW_DENSE = 5,   /* level flow after densification (before variational refinement) */
+  DIS_TAP_FLOW_REFINED = 6, /* level flow after variational refinement                      */
+  DIS_TAP_IMG_B_DX = 7,
+  DIS_TAP_IMG_B_DY = 8
+} dis_tap;
+/* Keeps per-level copies of the tapped buffers during the next runs (costs memory and time). */
+int dis_enable_taps(dis_handle* h, int on);
+int dis_fetch_tap(dis_handle* h, int tap, int level, float* out, size_t n_floats, size_t* n_written);
+
+/* Library identification: "dis_b200 <version> sm_100a". */
+const char* dis_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIS_C_H */
