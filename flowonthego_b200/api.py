@@ -1,0 +1,325 @@
+"""Python host-side mirror of the reference interface, on top of the C-ABI (include/dis_c.h).
+
+* ``Params``        -- struct dis_params: the 20 CLI parameters of kroeger/run_dense.cpp:271-291
+* ``Engine``        -- one dis_handle (one CUDA stream + workspace + CUDA graph)
+* ``OFClass(...)``  -- same positional arguments as ``OFC::OFClass::OFClass`` (kroeger/oflow.h:84-111)
+* ``run_dense(...)``-- the three call variants of the reference CLI (kroeger/README.md:48-88)
+
+Everything computes in libdis_b200.so (hand-written sm_100a kernels).  There is no CPU path:
+if the library is missing or no B200 is visible, calls raise.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libdis_b200.so")
+_LIB = None
+
+PARAM_NAMES = ("lv_f", "lv_l", "maxiter", "miniter", "mindprate", "mindrrate", "minimgerr", "patchsz",
+               "poverl", "usefbcon", "patnorm", "costfct", "usetvref", "tv_alpha", "tv_gamma", "tv_delta",
+               "tv_innerit", "tv_solverit", "tv_sor", "verbosity")
+_FLOAT_PARAMS = {"mindprate", "mindrrate", "minimgerr", "poverl", "tv_alpha", "tv_gamma", "tv_delta", "tv_sor"}
+
+# enum dis_tap
+TAP_IMG_A, TAP_IMG_A_DX, TAP_IMG_A_DY, TAP_IMG_B, TAP_PATCH_FLOW, TAP_FLOW_DENSE, TAP_FLOW_REFINED, \
+    TAP_IMG_B_DX, TAP_IMG_B_DY = range(9)
+
+
+class DisError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("dis error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Params(ctypes.Structure):
+    """struct dis_params (include/dis_c.h)."""
+    _fields_ = [(n, ctypes.c_float if n in _FLOAT_PARAMS else ctypes.c_int32) for n in PARAM_NAMES]
+
+    @classmethod
+    def from_dict(cls, d):
+        p = cls()
+        for n in PARAM_NAMES:
+            setattr(p, n, float(d[n]) if n in _FLOAT_PARAMS else int(d[n]))
+        return p
+
+    @classmethod
+    def preset(cls, preset, width_org, verbosity=0):
+        """Operating points 1..4, kroeger/run_dense.cpp:225-267."""
+        p = cls()
+        _check(lib().dis_params_preset(ctypes.byref(p), int(preset), int(width_org)), None)
+        p.verbosity = verbosity
+        return p
+
+    @classmethod
+    def from_argv(cls, args):
+        """20 explicit parameters in CLI order (strings), kroeger/run_dense.cpp:271-291."""
+        args = [str(a).encode() for a in args]
+        arr = (ctypes.c_char_p * len(args))(*args)
+        p = cls()
+        _check(lib().dis_params_from_argv(ctypes.byref(p), len(args), arr), None)
+        return p
+
+    def to_dict(self):
+        return {n: getattr(self, n) for n in PARAM_NAMES}
+
+    def copy(self, **kw):
+        d = self.to_dict()
+        d.update(kw)
+        return Params.from_dict(d)
+
+
+class Timings(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_float) for n in ("total_ms", "h2d_ms", "pyramid_ms", "search_ms", "densify_ms",
+                                               "varref_ms", "finish_ms", "d2h_ms")] + [("launches", ctypes.c_int32)]
+
+
+def lib():
+    """Loads libdis_b200.so; raises if it has not been built (no fallback of any kind)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(_LIB_PATH):
+            raise ImportError(_LIB_PATH + " not built: run `python -c 'import __graft_entry__ as g; g.build()'`"
+                              " or `make -C flowonthego_b200/csrc`")
+        L = ctypes.CDLL(_LIB_PATH)
+        vp, ip, fp = ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_float)
+        fpp = ctypes.POINTER(fp)
+        pp = ctypes.POINTER(Params)
+        L.dis_version.restype = ctypes.c_char_p
+        L.dis_last_error.restype = ctypes.c_char_p
+        L.dis_last_error.argtypes = [vp]
+        L.dis_params_preset.argtypes = [pp, ip, ip]
+        L.dis_params_from_argv.argtypes = [pp, ip, ctypes.POINTER(ctypes.c_char_p)]
+        L.dis_params_validate.argtypes = [pp, ctypes.c_char_p, ctypes.c_size_t]
+        L.dis_padded_size.argtypes = [ip, ip, ip] + [ctypes.POINTER(ip)] * 4
+        L.dis_auto_first_scale.argtypes = [ip, ip, ip]
+        L.dis_create.argtypes = [pp, ip, ip, ip, ctypes.POINTER(vp)]
+        L.dis_destroy.argtypes = [vp]
+        L.dis_set_params.argtypes = [vp, pp]
+        L.dis_run_pyramids.argtypes = [vp] + [fpp] * 6 + [ip, ip, ip, fp, fp]
+        L.dis_run_u8.argtypes = [vp, vp, vp, ip, ip, ip, fp]
+        L.dis_submit_u8.argtypes = [vp, vp, vp, ip, ip, ip, fp]
+        L.dis_submit_u8_device.argtypes = [vp, vp, vp, ip, ip, ip, vp]
+        L.dis_wait.argtypes = [vp]
+        L.dis_fetch_level_flow.argtypes = [vp, fp, ctypes.c_size_t]
+        L.dis_stream.restype = vp
+        L.dis_stream.argtypes = [vp]
+        L.dis_get_timings.argtypes = [vp, ctypes.POINTER(Timings)]
+        L.dis_enable_stage_timing.argtypes = [vp, ip]
+        L.dis_enable_taps.argtypes = [vp, ip]
+        L.dis_fetch_tap.argtypes = [vp, ip, ip, fp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
+        L.dis_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
+        L.dis_host_free.argtypes = [vp]
+        L.dis_write_flo.argtypes = [ctypes.c_char_p, fp, ip, ip]
+        L.dis_read_flo.argtypes = [ctypes.c_char_p, fp, ctypes.c_size_t, ctypes.POINTER(ip), ctypes.POINTER(ip)]
+        _LIB = L
+    return _LIB
+
+
+def _check(rc, handle):
+    if rc != 0:
+        msg = lib().dis_last_error(handle)
+        raise DisError(rc, msg.decode() if msg else "")
+
+
+_fp = ctypes.POINTER(ctypes.c_float)
+
+
+def _as_fp(a):
+    return a.ctypes.data_as(_fp)
+
+
+def padded_size(w, h, lv_f):
+    """(w_pad, h_pad, left, top) -- kroeger/run_dense.cpp:298-311."""
+    v = [ctypes.c_int() for _ in range(4)]
+    _check(lib().dis_padded_size(w, h, lv_f, *[ctypes.byref(x) for x in v]), None)
+    return tuple(x.value for x in v)
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by page-locked host memory (dis_host_alloc)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = ctypes.c_void_p()
+    if lib().dis_host_alloc(ctypes.byref(p), max(n, 1)) != 0:
+        raise MemoryError("dis_host_alloc(%d)" % n)
+    buf = (ctypes.c_char * max(n, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _PINNED[arr.ctypes.data] = p
+    return arr
+
+
+_PINNED = {}
+
+
+class Engine:
+    """One engine instance = one dis_handle (stream, workspace, CUDA graph)."""
+
+    def __init__(self, params, max_w, max_h, device=0):
+        self._h = ctypes.c_void_p()
+        self.params = params if isinstance(params, Params) else Params.from_dict(params)
+        _check(lib().dis_create(ctypes.byref(self.params), int(max_w), int(max_h), int(device),
+                                ctypes.byref(self._h)), None)
+        self._keep = None
+
+    def close(self):
+        if self._h:
+            lib().dis_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_params(self, params):
+        self.params = params if isinstance(params, Params) else Params.from_dict(params)
+        _check(lib().dis_set_params(self._h, ctypes.byref(self.params)), self._h)
+
+    # ---- whole run_dense data path ----------------------------------------------------------
+    def run_u8(self, a, b, out=None):
+        """Grey u8 frames (h, w) -> full-resolution flow (h, w, 2) float32. Synchronous."""
+        self.submit_u8(a, b, out)
+        return self.wait()
+
+    def submit_u8(self, a, b, out=None):
+        a = np.ascontiguousarray(a, np.uint8) if not (a.dtype == np.uint8 and a.strides[1] == 1) else a
+        b = np.ascontiguousarray(b, np.uint8) if not (b.dtype == np.uint8 and b.strides[1] == 1) else b
+        if a.ndim != 2 or a.shape != b.shape or a.strides[0] != b.strides[0]:
+            raise ValueError("need two grey u8 images of identical shape and pitch")
+        h, w = a.shape
+        if out is None:
+            out = np.empty((h, w, 2), np.float32)
+        self._keep = (a, b, out)
+        _check(lib().dis_submit_u8(self._h, a.ctypes.data, b.ctypes.data, w, h, a.strides[0], _as_fp(out)), self._h)
+
+    def submit_u8_device(self, d_a, d_b, w, h, pitch, d_flow):
+        """Device pointers (ints) in, device pointer out; asynchronous on the engine's stream."""
+        _check(lib().dis_submit_u8_device(self._h, d_a, d_b, w, h, pitch, d_flow), self._h)
+
+    def wait(self):
+        _check(lib().dis_wait(self._h), self._h)
+        keep, self._keep = self._keep, None
+        return keep[2] if keep else None
+
+    def level_flow(self, w, h):
+        """Raw engine output (level lv_l, padded size) of the last run_u8."""
+        wp, hp, _, _ = padded_size(w, h, self.params.lv_f)
+        sc = 1 << self.params.lv_l
+        out = np.empty((hp // sc, wp // sc, 2), np.float32)
+        _check(lib().dis_fetch_level_flow(self._h, _as_fp(out), out.size), self._h)
+        return out
+
+    # ---- the reference engine boundary ------------------------------------------------------
+    def run_pyramids(self, pyr_a, pyr_b, width, height, initflow=None):
+        """pyr_a/pyr_b = (I, Ix, Iy): lists over levels 0..lv_f of padded float32 arrays (entries below
+        lv_l may be None).  Returns flow (height/2^lv_l, width/2^lv_l, 2)."""
+        p = self.params
+        ptrs, keep = [], []
+        for lst in (*pyr_a, *pyr_b):
+            arr = (_fp * (p.lv_f + 1))()
+            for l in range(p.lv_f + 1):
+                x = lst[l] if lst is not None and l < len(lst) else None
+                if x is not None:
+                    x = np.ascontiguousarray(x, np.float32)
+                    keep.append(x)
+                    arr[l] = _as_fp(x)
+            ptrs.append(arr)
+        sc = 1 << p.lv_l
+        out = np.empty((height // sc, width // sc, 2), np.float32)
+        init = None
+        if initflow is not None:
+            initflow = np.ascontiguousarray(initflow, np.float32)
+            init = _as_fp(initflow)
+        _check(lib().dis_run_pyramids(self._h, *ptrs, p.patchsz, width, height, init, _as_fp(out)), self._h)
+        return out
+
+    # ---- introspection ------------------------------------------------------------------------
+    def enable_taps(self, on=True):
+        _check(lib().dis_enable_taps(self._h, int(on)), self._h)
+
+    def enable_stage_timing(self, on=True):
+        _check(lib().dis_enable_stage_timing(self._h, int(on)), self._h)
+
+    def tap(self, which, level):
+        n = ctypes.c_size_t()
+        _check(lib().dis_fetch_tap(self._h, which, level, None, 0, ctypes.byref(n)), self._h)
+        out = np.empty(n.value, np.float32)
+        _check(lib().dis_fetch_tap(self._h, which, level, _as_fp(out), out.size, ctypes.byref(n)), self._h)
+        return out
+
+    def timings(self):
+        t = Timings()
+        _check(lib().dis_get_timings(self._h, ctypes.byref(t)), self._h)
+        return {n: getattr(t, n) for n, _ in Timings._fields_}
+
+    @property
+    def stream(self):
+        return lib().dis_stream(self._h)
+
+
+def OFClass(im_ao, im_ao_dx, im_ao_dy, im_bo, im_bo_dx, im_bo_dy, imgpadding, outflow, initflow, width, height,
+            sc_f, sc_l, max_iter, min_iter, dp_thresh, dr_thresh, res_thresh, p_samp_s, patove, usefbcon, costfct,
+            noc, patnorm, usetvref, tv_alpha, tv_gamma, tv_delta, tv_innerit, tv_solverit, tv_sor, verbosity,
+            device=0):
+    """Same positional arguments as ``OFC::OFClass::OFClass`` (kroeger/oflow.h:84-111); like the
+    reference, all work happens in this call and the result is written into ``outflow``."""
+    if noc != 1:
+        raise DisError(2, "only noc=1 (grey, SELECTCHANNEL=1) is supported")
+    if imgpadding != p_samp_s:
+        raise DisError(2, "imgpadding must equal the patch size (kroeger/run_dense.cpp:393)")
+    p = Params.from_dict(dict(lv_f=sc_f, lv_l=sc_l, maxiter=max_iter, miniter=min_iter, mindprate=dp_thresh,
+                              mindrrate=dr_thresh, minimgerr=res_thresh, patchsz=p_samp_s, poverl=patove,
+                              usefbcon=int(usefbcon), patnorm=patnorm, costfct=costfct, usetvref=int(usetvref),
+                              tv_alpha=tv_alpha, tv_gamma=tv_gamma, tv_delta=tv_delta, tv_innerit=tv_innerit,
+                              tv_solverit=tv_solverit, tv_sor=tv_sor, verbosity=verbosity))
+    with Engine(p, width, height, device) as e:
+        fl = e.run_pyramids((im_ao, im_ao_dx, im_ao_dy), (im_bo, im_bo_dx, im_bo_dy), width, height, initflow)
+    np.asarray(outflow).reshape(fl.shape)[...] = fl
+    return outflow
+
+
+def write_flo(path, flow):
+    flow = np.ascontiguousarray(flow, np.float32)
+    h, w = flow.shape[:2]
+    _check(lib().dis_write_flo(os.fsencode(path), _as_fp(flow), w, h), None)
+
+
+def read_flo(path):
+    w, h = ctypes.c_int(), ctypes.c_int()
+    _check(lib().dis_read_flo(os.fsencode(path), None, 0, ctypes.byref(w), ctypes.byref(h)), None)
+    out = np.empty((h.value, w.value, 2), np.float32)
+    _check(lib().dis_read_flo(os.fsencode(path), _as_fp(out), out.size, ctypes.byref(w), ctypes.byref(h)), None)
+    return out
+
+
+def run_dense(img1, img2, outfile, *args, device=0):
+    """``run_dense img1 img2 out [X | 20 params]`` -- the reference CLI variants (kroeger/README.md:48-88).
+    img1/img2 are file names (decoded with cv2.imread(..., IMREAD_GRAYSCALE) like the reference,
+    kroeger/run_dense.cpp:208-209) or already-decoded grey u8 arrays."""
+    def load(x):
+        if isinstance(x, np.ndarray):
+            return x
+        import cv2
+        im = cv2.imread(x, cv2.IMREAD_GRAYSCALE)
+        if im is None:
+            raise DisError(4, "cannot read " + str(x))
+        return im
+    a, b = load(img1), load(img2)
+    if len(args) <= 1:
+        p = Params.preset(int(args[0]) if args else 2, a.shape[1], verbosity=2)
+    else:
+        p = Params.from_argv(args)
+    with Engine(p, a.shape[1], a.shape[0], device) as e:
+        flow = e.run_u8(a, b)
+    if outfile is not None:
+        write_flo(outfile, flow)
+    return flow

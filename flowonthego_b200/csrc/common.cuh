@@ -1,0 +1,79 @@
+// common.cuh -- shared declarations for the sm_100a kernels of libdis_b200.so.
+//
+// Arithmetic contract: every translation unit is compiled with
+// -fmad=false (no FMA contraction), IEEE div/sqrt (nvcc defaults -prec-div/-prec-sqrt=true),
+// no flush-to-zero, so that `a*b + c` rounds twice exactly like the reference's -msse4 build.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dis {
+
+// Geometry of one pyramid level (reference: camparam, kroeger/oflow.h:16-29; grid geometry
+// kroeger/patchgrid.cpp:42-49).
+struct LevelGeom {
+  int lv;          // pyramid level
+  int w, h;        // unpadded level size
+  int pad;         // image padding (= patch size)
+  int pitch;       // row pitch of the padded images, in floats (multiple of 32)
+  int tw, th;      // padded size w+2*pad, h+2*pad
+  float lb, ubw, ubh;  // valid region for patch centres (oflow.cpp:147-149)
+  int nopw, noph, offw, offh, nop;  // patch grid
+  int fpitch;      // pitch (in pixels) of per-level planar/float2 work images (= w)
+};
+
+// Parameters derived in OFClass::OFClass (kroeger/oflow.cpp:75-108)
+struct OptParams {
+  int p, novals, steps, max_iter, min_iter, patnorm, costfct;
+  float outlierthresh, dp_thresh, dr_thresh, res_thresh;
+};
+
+struct VarParams {  // kroeger/refine_variational.cpp:28-42
+  float qa, hg, hd, omega;
+  int n_inner, n_solver;
+};
+
+// ---- launchers (defined in the .cu files) --------------------------------------------------
+// pyramid.cu
+void launch_level0(const uint8_t* src_a, const uint8_t* src_b, int w_org, int h_org, int src_pitch,
+                   int left, int top, const LevelGeom& g, float* Ia, float* Iax, float* Iay,
+                   float* Ib, float* Ibx, float* Iby, cudaStream_t st);
+void launch_downsample(const LevelGeom& gf, const LevelGeom& gc, const float* Ia_f, const float* Ib_f,
+                       float* Ia, float* Iax, float* Iay, float* Ib, float* Ibx, float* Iby,
+                       cudaStream_t st);
+// patch_search.cu
+struct PatchSearchArgs {
+  const float *I0, *I0x, *I0y, *I1;
+  LevelGeom g;
+  OptParams o;
+  const float2* flow_coarse;  // level l+1 dense flow (or initflow); nullptr -> zero init
+  float2* pflow;              // nop
+  float* pweight;             // nop * novals
+};
+int launch_patch_search(const PatchSearchArgs& a, cudaStream_t st);
+// densify.cu
+struct DensifyArgs {
+  LevelGeom g;
+  OptParams o;
+  const float2* pflow;
+  const float* pweight;
+  const float2* pflow_bw;   // complementary grid (forward-backward merge) or nullptr
+  const float* pweight_bw;
+  float2* flow;             // w*h
+};
+void launch_densify(const DensifyArgs& a, cudaStream_t st);
+// varref.cu
+struct VarRefBuffers {
+  float *avg, *Iz, *mask, *Ix, *Iy, *Ixx, *Ixy, *Iyy, *Ixz, *Iyz;  // planar, w*h
+  float *a11, *a12, *a22;                                          // inverted 2x2 blocks
+  float2 *b, *hv, *duv;                                            // (b1,b2), (horiz,vert), (du,dv)
+  int* progress;                                                   // SOR wavefront flags
+};
+int launch_varref(const LevelGeom& g, const VarParams& v, const float* I0, const float* I1,
+                  float2* flow, const VarRefBuffers& b, cudaStream_t st);
+size_t varref_progress_ints(int h, int n_solver);
+// finish.cu
+void launch_finish(const float2* flow_l, int wl, int hl, int lv_l, int left, int top, int w_org,
+                   int h_org, float2* out, cudaStream_t st);
+
+}  // namespace dis

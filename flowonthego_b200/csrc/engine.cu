@@ -1,0 +1,827 @@
+// engine.cu -- host side of libdis_b200.so: the C-ABI of include/dis_c.h.
+//
+// Mirrors the control flow of the reference engine OFC::OFClass::OFClass
+// (kroeger/oflow.cpp:32-363): derive the optimisation parameters (:75-108), lay out one
+// `camparam` per scale (:138-160), then run the coarse-to-fine loop (:184-337)
+//     search (InitializeGrid/SetTargetImage/InitializeFromCoarserOF/Optimize) -> densify -> refine
+// with every stage a CUDA kernel on the handle's stream.  The driver part of the reference CLI
+// that sits between imread and SaveFlowFile (kroeger/run_dense.cpp:298-414) is covered by
+// dis_run_u8 / dis_submit_u8*: padding, pyramid and gradients, engine, upsampling, crop.
+//
+// All device memory is one slab planned per (image size, parameter set); a whole run is
+// recorded once into a CUDA graph and replayed (the coarse levels are launch-latency bound).
+// There is no CPU fallback anywhere: if CUDA is unavailable every entry point fails.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dis_c.h"
+#include "common.cuh"
+
+using namespace dis;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct LevelBufs {
+  LevelGeom g{};
+  float *Ia = nullptr, *Iax = nullptr, *Iay = nullptr, *Ib = nullptr, *Ibx = nullptr, *Iby = nullptr;
+  float2 *flow = nullptr, *flow_bw = nullptr;
+};
+
+struct Tap {
+  std::vector<float> data;
+};
+
+}  // namespace
+
+struct dis_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  dis_params P{};
+  OptParams opt{};
+  int max_w = 0, max_h = 0;
+  std::string err;
+
+  // current plan
+  int w_org = 0, h_org = 0, w_pad = 0, h_pad = 0, left = 0, top = 0;
+  std::vector<LevelBufs> lv;  // index = level
+  uint8_t *d_a = nullptr, *d_b = nullptr;
+  float2 *pflow = nullptr, *pflow_bw = nullptr;
+  float *pweight = nullptr, *pweight_bw = nullptr;
+  VarRefBuffers vb{};
+  float2* d_out = nullptr;
+  char* slab = nullptr;
+  size_t slab_bytes = 0;
+
+  // graph
+  bool use_graph = true;
+  cudaGraphExec_t graph_exec = nullptr;
+  int graph_w = 0, graph_h = 0;
+  const void *graph_a = nullptr, *graph_b = nullptr, *graph_out = nullptr;
+
+  // timing / taps
+  bool stage_timing = false;
+  bool taps = false;
+  std::vector<std::vector<Tap>> tapdata;  // [tap][level]
+  dis_timings tm{};
+  cudaEvent_t ev[10] = {};
+  int launches = 0;
+  bool in_flight = false;
+};
+
+namespace {
+
+int fail(dis_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h)
+    h->err = buf;
+  else
+    g_create_error = buf;
+  return code;
+}
+
+#define CU(h, call)                                                                           \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(h, DIS_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                  __LINE__);                                                                  \
+  } while (0)
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// kroeger/oflow.cpp:75-108
+void derive_opt(const dis_params& q, OptParams* o) {
+  o->p = q.patchsz;
+  o->outlierthresh = (float)o->p / 2;
+  o->max_iter = q.maxiter;
+  o->min_iter = q.miniter;
+  o->dp_thresh = q.mindprate * q.mindprate;
+  o->dr_thresh = q.mindrrate;
+  o->res_thresh = q.minimgerr;
+  o->steps = std::max(1, (int)floor(o->p * (1 - q.poverl)));
+  o->novals = o->p * o->p;
+  o->patnorm = q.patnorm;
+  o->costfct = q.costfct;
+}
+
+// kroeger/oflow.cpp:138-160 (camparam) and kroeger/patchgrid.cpp:42-49 (grid geometry)
+void derive_level(const OptParams& o, int width, int height, int pad, int sl, LevelGeom* g) {
+  const float sc_fct = (float)pow(2, -sl);
+  g->lv = sl;
+  g->h = (int)(height * sc_fct);
+  g->w = (int)(width * sc_fct);
+  g->pad = pad;
+  g->tw = g->w + 2 * pad;
+  g->th = g->h + 2 * pad;
+  g->pitch = (int)align_up((size_t)g->tw, 32);
+  g->lb = -(float)o.p / 2;
+  g->ubw = (float)(g->w + o.p / 2 - 2);
+  g->ubh = (float)(g->h + o.p / 2 - 2);
+  g->nopw = (int)ceil((float)g->w / (float)o.steps);
+  g->noph = (int)ceil((float)g->h / (float)o.steps);
+  g->offw = (int)floor((g->w - (g->nopw - 1) * o.steps) / 2);
+  g->offh = (int)floor((g->h - (g->noph - 1) * o.steps) / 2);
+  g->nop = g->nopw * g->noph;
+  g->fpitch = g->w;
+}
+
+struct Carver {
+  char* base;
+  size_t off = 0;
+  template <typename T>
+  T* take(size_t n) {
+    off = align_up(off, 256);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+// Lays out every buffer of a run for input size (w,h); with base == nullptr only sizes it.
+size_t carve(dis_handle* h, int w, int h_img, char* base, bool assign) {
+  const dis_params& q = h->P;
+  int wp, hp, left, top;
+  dis_padded_size(w, h_img, q.lv_f, &wp, &hp, &left, &top);
+  Carver c{base};
+  std::vector<LevelBufs> lv(q.lv_f + 1);
+  uint8_t* d_a = c.take<uint8_t>((size_t)w * h_img);
+  uint8_t* d_b = c.take<uint8_t>((size_t)w * h_img);
+  for (int l = 0; l <= q.lv_f; ++l) {
+    LevelBufs& L = lv[l];
+    derive_level(h->opt, wp, hp, q.patchsz, l, &L.g);
+    const size_t n = (size_t)L.g.pitch * L.g.th;
+    L.Ia = c.take<float>(n);
+    L.Ib = c.take<float>(n);
+    if (l >= q.lv_l) {
+      L.Iax = c.take<float>(n);
+      L.Iay = c.take<float>(n);
+      if (q.usefbcon) {
+        L.Ibx = c.take<float>(n);
+        L.Iby = c.take<float>(n);
+      }
+      L.flow = c.take<float2>((size_t)L.g.w * L.g.h);
+      if (q.usefbcon) L.flow_bw = c.take<float2>((size_t)L.g.w * L.g.h);
+    }
+  }
+  const LevelGeom& gf = lv[q.lv_l].g;  // finest processed level = largest buffers
+  float2* pflow = c.take<float2>(gf.nop);
+  float* pweight = c.take<float>((size_t)gf.nop * h->opt.novals);
+  float2* pflow_bw = nullptr;
+  float* pweight_bw = nullptr;
+  if (q.usefbcon) {
+    pflow_bw = c.take<float2>(gf.nop);
+    pweight_bw = c.take<float>((size_t)gf.nop * h->opt.novals);
+  }
+  VarRefBuffers vb{};
+  if (q.usetvref) {
+    const size_t n = (size_t)gf.w * gf.h;
+    float** planes[] = {&vb.avg, &vb.Iz, &vb.mask, &vb.Ix, &vb.Iy, &vb.Ixx, &vb.Ixy,
+                        &vb.Iyy, &vb.Ixz, &vb.Iyz, &vb.a11, &vb.a12, &vb.a22};
+    for (float** p : planes) *p = c.take<float>(n);
+    vb.b = c.take<float2>(n);
+    vb.hv = c.take<float2>(n);
+    vb.duv = c.take<float2>(n);
+    vb.progress = c.take<int>(varref_progress_ints(gf.h, std::max(1, q.tv_solverit)));
+  }
+  float2* d_out = c.take<float2>((size_t)w * h_img);
+  if (assign) {
+    h->lv = lv;
+    h->d_a = d_a;
+    h->d_b = d_b;
+    h->pflow = pflow;
+    h->pweight = pweight;
+    h->pflow_bw = pflow_bw;
+    h->pweight_bw = pweight_bw;
+    h->vb = vb;
+    h->d_out = d_out;
+    h->w_org = w;
+    h->h_org = h_img;
+    h->w_pad = wp;
+    h->h_pad = hp;
+    h->left = left;
+    h->top = top;
+  }
+  return align_up(c.off, 256);
+}
+
+void drop_graph(dis_handle* h) {
+  if (h->graph_exec) {
+    cudaGraphExecDestroy(h->graph_exec);
+    h->graph_exec = nullptr;
+  }
+}
+
+int plan(dis_handle* h, int w, int h_img) {
+  if (w <= 0 || h_img <= 0) return fail(h, DIS_ERR_INVALID_ARG, "non-positive image size %dx%d", w, h_img);
+  if (w == h->w_org && h_img == h->h_org && !h->lv.empty()) return DIS_OK;
+  const size_t need = carve(h, w, h_img, nullptr, false);
+  if (need > h->slab_bytes) {  // grow the slab (sizes above the create-time maximum re-allocate)
+    drop_graph(h);
+    if (h->slab) {
+      CU(h, cudaStreamSynchronize(h->stream));
+      cudaFree(h->slab);
+    }
+    h->slab = nullptr;
+    h->slab_bytes = 0;
+    CU(h, cudaMalloc(&h->slab, need));
+    h->slab_bytes = need;
+  }
+  drop_graph(h);
+  carve(h, w, h_img, h->slab, true);
+  // coarsest level must be large enough for the kernels (and for the reference itself)
+  const LevelGeom& gc = h->lv[h->P.lv_f].g;
+  if (gc.w < 2 || gc.h < 4)
+    return fail(h, DIS_ERR_UNSUPPORTED, "coarsest level %dx%d too small (lv_f=%d)", gc.w, gc.h, h->P.lv_f);
+  return DIS_OK;
+}
+
+void tap_store(dis_handle* h, int tap, int level, const void* dptr, size_t n_floats) {
+  if (!h->taps) return;
+  if ((int)h->tapdata.size() <= tap) h->tapdata.resize(tap + 1);
+  if ((int)h->tapdata[tap].size() <= level) h->tapdata[tap].resize(level + 1);
+  auto& v = h->tapdata[tap][level].data;
+  v.resize(n_floats);
+  cudaMemcpyAsync(v.data(), dptr, n_floats * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+  cudaStreamSynchronize(h->stream);
+}
+
+void tap_image(dis_handle* h, int tap, int level, const float* d, const LevelGeom& g) {
+  if (!h->taps || d == nullptr) return;
+  if ((int)h->tapdata.size() <= tap) h->tapdata.resize(tap + 1);
+  if ((int)h->tapdata[tap].size() <= level) h->tapdata[tap].resize(level + 1);
+  auto& v = h->tapdata[tap][level].data;
+  v.resize((size_t)g.tw * g.th);
+  cudaMemcpy2DAsync(v.data(), sizeof(float) * g.tw, d, sizeof(float) * g.pitch, sizeof(float) * g.tw, g.th,
+                    cudaMemcpyDeviceToHost, h->stream);
+  cudaStreamSynchronize(h->stream);
+}
+
+// stage 1 (kroeger/run_dense.cpp:298-344): pyramids of both frames from the u8 inputs
+int enqueue_pyramids(dis_handle* h, const uint8_t* d_a, const uint8_t* d_b, int src_pitch) {
+  const dis_params& q = h->P;
+  for (int l = 0; l <= q.lv_f; ++l) {
+    LevelBufs& L = h->lv[l];
+    if (l == 0)
+      launch_level0(d_a, d_b, h->w_org, h->h_org, src_pitch, h->left, h->top, L.g, L.Ia, L.Iax, L.Iay, L.Ib,
+                    L.Ibx, L.Iby, h->stream);
+    else
+      launch_downsample(h->lv[l - 1].g, L.g, h->lv[l - 1].Ia, h->lv[l - 1].Ib, L.Ia, L.Iax, L.Iay, L.Ib,
+                        L.Ibx, L.Iby, h->stream);
+    h->launches++;
+  }
+  if (h->taps)
+    for (int l = 0; l <= q.lv_f; ++l) {
+      LevelBufs& L = h->lv[l];
+      tap_image(h, DIS_TAP_IMG_A, l, L.Ia, L.g);
+      tap_image(h, DIS_TAP_IMG_A_DX, l, L.Iax, L.g);
+      tap_image(h, DIS_TAP_IMG_A_DY, l, L.Iay, L.g);
+      tap_image(h, DIS_TAP_IMG_B, l, L.Ib, L.g);
+      tap_image(h, DIS_TAP_IMG_B_DX, l, L.Ibx, L.g);
+      tap_image(h, DIS_TAP_IMG_B_DY, l, L.Iby, L.g);
+    }
+  return DIS_OK;
+}
+
+struct StageClock {
+  dis_handle* h;
+  bool on;
+  cudaEvent_t a = nullptr, b = nullptr;
+  float* acc;
+  StageClock(dis_handle* h_, float* acc_) : h(h_), on(h_->stage_timing), acc(acc_) {
+    if (on) {
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      cudaEventRecord(a, h->stream);
+    }
+  }
+  float stop() {
+    float ms = 0.f;
+    if (on) {
+      cudaEventRecord(b, h->stream);
+      cudaEventSynchronize(b);
+      cudaEventElapsedTime(&ms, a, b);
+      *acc += ms;
+      cudaEventDestroy(a);
+      cudaEventDestroy(b);
+      on = false;
+    }
+    return ms;
+  }
+  ~StageClock() { stop(); }
+};
+
+// the coarse-to-fine loop, kroeger/oflow.cpp:184-337
+int enqueue_engine(dis_handle* h, const float2* d_initflow) {
+  const dis_params& q = h->P;
+  VarParams vp{};
+  vp.qa = 0.25f * q.tv_alpha;               // refine_variational.cpp:40-42
+  vp.hg = q.tv_gamma * 0.5f / 3.0f;
+  vp.hd = q.tv_delta * 0.5f / 3.0f;
+  vp.omega = q.tv_sor;
+  vp.n_solver = q.tv_solverit;
+  for (int sl = q.lv_f; sl >= q.lv_l; --sl) {
+    LevelBufs& L = h->lv[sl];
+    float t_search = 0, t_dens = 0, t_var = 0;
+    const float2* coarse = nullptr;
+    if (sl < q.lv_f)
+      coarse = h->lv[sl + 1].flow;
+    else if (d_initflow)
+      coarse = d_initflow;
+    {
+      StageClock ck(h, &h->tm.search_ms);
+      PatchSearchArgs pa{L.Ia, L.Iax, L.Iay, L.Ib, L.g, h->opt, coarse, h->pflow, h->pweight};
+      if (launch_patch_search(pa, h->stream)) return fail(h, DIS_ERR_UNSUPPORTED, "patch size %d", h->opt.p);
+      h->launches++;
+      t_search = ck.stop();
+    }
+    tap_store(h, DIS_TAP_PATCH_FLOW, sl, h->pflow, (size_t)L.g.nop * 2);
+    {
+      StageClock ck(h, &h->tm.densify_ms);
+      DensifyArgs da{L.g, h->opt, h->pflow, h->pweight, nullptr, nullptr, L.flow};
+      launch_densify(da, h->stream);
+      h->launches++;
+      t_dens = ck.stop();
+    }
+    tap_store(h, DIS_TAP_FLOW_DENSE, sl, L.flow, (size_t)L.g.w * L.g.h * 2);
+    if (q.usetvref) {
+      StageClock ck(h, &h->tm.varref_ms);
+      vp.n_inner = q.tv_innerit * (sl + 1);  // refine_variational.cpp:36
+      const int n = launch_varref(L.g, vp, L.Ia, L.Ib, L.flow, h->vb, h->stream);
+      if (n < 0) return fail(h, DIS_ERR_UNSUPPORTED, "level %d (%dx%d) too small for refinement", sl, L.g.w, L.g.h);
+      h->launches += n;
+      t_var = ck.stop();
+    }
+    tap_store(h, DIS_TAP_FLOW_REFINED, sl, L.flow, (size_t)L.g.w * L.g.h * 2);
+    if (q.verbosity > 1 && h->stage_timing)  // format of kroeger/oflow.cpp:303
+      printf("TIME (Sc: %i, #p:%6i, pconst, pinit, poptim, cflow, tvopt, total): %8.2f %8.2f %8.2f %8.2f %8.2f -> %8.2f ms.\n",
+             sl, L.g.nop, 0.0, 0.0, t_search, t_dens, t_var, t_search + t_dens + t_var);
+  }
+  CU(h, cudaGetLastError());
+  return DIS_OK;
+}
+
+int enqueue_finish(dis_handle* h, float2* d_out) {
+  const LevelBufs& L = h->lv[h->P.lv_l];
+  launch_finish(L.flow, L.g.w, L.g.h, h->P.lv_l, h->left, h->top, h->w_org, h->h_org, d_out, h->stream);
+  h->launches++;
+  CU(h, cudaGetLastError());
+  return DIS_OK;
+}
+
+// Enqueue the whole device-side run (stage 1 .. finish); replayed from a CUDA graph when possible.
+int enqueue_run_device(dis_handle* h, const uint8_t* d_a, const uint8_t* d_b, int pitch, float2* d_out) {
+  const bool graphable = h->use_graph && !h->taps && !h->stage_timing;
+  if (graphable && h->graph_exec && h->graph_a == d_a && h->graph_b == d_b && h->graph_out == d_out &&
+      h->graph_w == h->w_org && h->graph_h == h->h_org) {
+    CU(h, cudaGraphLaunch(h->graph_exec, h->stream));
+    return DIS_OK;
+  }
+  if (graphable) {
+    drop_graph(h);
+    h->launches = 0;
+    CU(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_pyramids(h, d_a, d_b, pitch);
+    if (rc == DIS_OK) rc = enqueue_engine(h, nullptr);
+    if (rc == DIS_OK) rc = enqueue_finish(h, d_out);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+    if (rc != DIS_OK) {
+      if (g) cudaGraphDestroy(g);
+      return rc;
+    }
+    if (e != cudaSuccess) return fail(h, DIS_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&h->graph_exec, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(h, DIS_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+    h->graph_a = d_a;
+    h->graph_b = d_b;
+    h->graph_out = d_out;
+    h->graph_w = h->w_org;
+    h->graph_h = h->h_org;
+    h->tm.launches = h->launches;
+    CU(h, cudaGraphLaunch(h->graph_exec, h->stream));
+    return DIS_OK;
+  }
+  h->launches = 0;
+  int rc;
+  {
+    StageClock ck(h, &h->tm.pyramid_ms);
+    rc = enqueue_pyramids(h, d_a, d_b, pitch);
+  }
+  if (rc == DIS_OK) rc = enqueue_engine(h, nullptr);
+  if (rc == DIS_OK) {
+    StageClock ck(h, &h->tm.finish_ms);
+    rc = enqueue_finish(h, d_out);
+  }
+  h->tm.launches = h->launches;
+  return rc;
+}
+
+void reset_timings(dis_handle* h) {
+  const int l = h->tm.launches;
+  h->tm = dis_timings{};
+  h->tm.launches = l;
+}
+
+}  // namespace
+
+// ================================================================================ C-ABI
+extern "C" {
+
+const char* dis_version(void) { return "dis_b200 0.1 sm_100a"; }
+
+int dis_auto_first_scale(int imgwidth, int fratio, int patchsize) {
+  return std::max(0, (int)std::floor(log2((2.0f * (float)imgwidth) / ((float)fratio * (float)patchsize))));
+}
+
+int dis_params_preset(dis_params* p, int preset, int width_org) {
+  if (!p || width_org <= 0) return DIS_ERR_INVALID_ARG;
+  // defaults, kroeger/run_dense.cpp:227-233
+  p->mindprate = 0.05f;
+  p->mindrrate = 0.95f;
+  p->minimgerr = 0.0f;
+  p->usefbcon = 0;
+  p->patnorm = 1;
+  p->costfct = 0;
+  p->tv_alpha = 10.0f;
+  p->tv_gamma = 10.0f;
+  p->tv_delta = 5.0f;
+  p->tv_innerit = 1;
+  p->tv_solverit = 3;
+  p->tv_sor = 1.6f;
+  p->verbosity = 2;
+  const int fratio = 5;
+  switch (preset) {  // run_dense.cpp:239-267
+    case 1:
+      p->patchsz = 8; p->poverl = 0.3f;
+      p->lv_f = dis_auto_first_scale(width_org, fratio, p->patchsz);
+      p->lv_l = std::max(p->lv_f - 2, 0); p->maxiter = 16; p->miniter = 16; p->usetvref = 0;
+      break;
+    case 3:
+      p->patchsz = 12; p->poverl = 0.75f;
+      p->lv_f = dis_auto_first_scale(width_org, fratio, p->patchsz);
+      p->lv_l = std::max(p->lv_f - 4, 0); p->maxiter = 16; p->miniter = 16; p->usetvref = 1;
+      break;
+    case 4:
+      p->patchsz = 12; p->poverl = 0.75f;
+      p->lv_f = dis_auto_first_scale(width_org, fratio, p->patchsz);
+      p->lv_l = std::max(p->lv_f - 5, 0); p->maxiter = 128; p->miniter = 128; p->usetvref = 1;
+      break;
+    case 2:
+    default:
+      p->patchsz = 8; p->poverl = 0.4f;
+      p->lv_f = dis_auto_first_scale(width_org, fratio, p->patchsz);
+      p->lv_l = std::max(p->lv_f - 2, 0); p->maxiter = 12; p->miniter = 12; p->usetvref = 1;
+      break;
+  }
+  return DIS_OK;
+}
+
+int dis_params_from_argv(dis_params* p, int n, const char* const* a) {
+  if (!p || !a || n < 20) return DIS_ERR_INVALID_ARG;
+  int k = 0;  // order of kroeger/run_dense.cpp:271-291
+  p->lv_f = atoi(a[k++]);
+  p->lv_l = atoi(a[k++]);
+  p->maxiter = atoi(a[k++]);
+  p->miniter = atoi(a[k++]);
+  p->mindprate = (float)atof(a[k++]);
+  p->mindrrate = (float)atof(a[k++]);
+  p->minimgerr = (float)atof(a[k++]);
+  p->patchsz = atoi(a[k++]);
+  p->poverl = (float)atof(a[k++]);
+  p->usefbcon = atoi(a[k++]) != 0;
+  p->patnorm = atoi(a[k++]);
+  p->costfct = atoi(a[k++]);
+  p->usetvref = atoi(a[k++]) != 0;
+  p->tv_alpha = (float)atof(a[k++]);
+  p->tv_gamma = (float)atof(a[k++]);
+  p->tv_delta = (float)atof(a[k++]);
+  p->tv_innerit = atoi(a[k++]);
+  p->tv_solverit = atoi(a[k++]);
+  p->tv_sor = (float)atof(a[k++]);
+  p->verbosity = atoi(a[k++]);
+  return DIS_OK;
+}
+
+int dis_params_validate(const dis_params* p, char* why, size_t why_len) {
+  const char* msg = nullptr;
+  if (!p) msg = "null params";
+  else if (p->lv_l < 0 || p->lv_f < p->lv_l || p->lv_f > 14) msg = "need 0 <= lv_l <= lv_f <= 14";
+  else if (p->patchsz < 4 || p->patchsz > 16 || (p->patchsz & 1)) msg = "patchsz must be even and in 4..16";
+  else if (!(p->poverl >= 0.0f && p->poverl < 1.0f)) msg = "poverl must be in [0,1)";
+  else if (p->costfct < 0 || p->costfct > 2) msg = "costfct must be 0 (L2), 1 (L1) or 2 (Huber)";
+  else if (p->maxiter < 0 || p->miniter < 0) msg = "negative iteration count";
+  else if (p->usetvref && p->tv_solverit < 1) msg = "tv_solverit must be >= 1";
+  else if (p->usetvref && p->tv_innerit < 0) msg = "tv_innerit must be >= 0";
+  else if (p->usefbcon) msg = "usefbcon=1 (forward-backward merging) is not implemented yet";
+  if (msg) {
+    if (why && why_len) snprintf(why, why_len, "%s", msg);
+    return p && p->usefbcon && msg[0] == 'u' ? DIS_ERR_UNSUPPORTED : DIS_ERR_INVALID_ARG;
+  }
+  if (why && why_len) why[0] = 0;
+  return DIS_OK;
+}
+
+int dis_padded_size(int w, int h, int lv_f, int* w_pad, int* h_pad, int* left, int* top) {
+  if (w <= 0 || h <= 0 || lv_f < 0 || lv_f > 14) return DIS_ERR_INVALID_ARG;
+  const int sc = 1 << lv_f;  // kroeger/run_dense.cpp:298-311
+  int padw = 0, padh = 0;
+  if (w % sc) padw = sc - w % sc;
+  if (h % sc) padh = sc - h % sc;
+  if (w_pad) *w_pad = w + padw;
+  if (h_pad) *h_pad = h + padh;
+  if (left) *left = (int)floorf((float)padw / 2.0f);
+  if (top) *top = (int)floorf((float)padh / 2.0f);
+  return DIS_OK;
+}
+
+const char* dis_last_error(const dis_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int dis_create(const dis_params* params, int max_w, int max_h, int device, dis_handle** out) {
+  if (!out) return fail(nullptr, DIS_ERR_INVALID_ARG, "out is null");
+  *out = nullptr;
+  char why[128];
+  int rc = dis_params_validate(params, why, sizeof why);
+  if (rc != DIS_OK) return fail(nullptr, rc, "invalid parameters: %s", why);
+  if (max_w <= 0 || max_h <= 0) return fail(nullptr, DIS_ERR_INVALID_ARG, "non-positive max size");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, DIS_ERR_CUDA, "no CUDA device available (%s); this library has no CPU path",
+                cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(nullptr, DIS_ERR_INVALID_ARG, "device %d out of range", device);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+    return fail(nullptr, DIS_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, DIS_ERR_UNSUPPORTED, "device %d is sm_%d%d; kernels are built for sm_100a only", device,
+                prop.major, prop.minor);
+  dis_handle* h = new dis_handle;
+  h->device = device;
+  h->P = *params;
+  derive_opt(h->P, &h->opt);
+  h->max_w = max_w;
+  h->max_h = max_h;
+  if ((e = cudaSetDevice(device)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    fail(nullptr, DIS_ERR_CUDA, "stream creation: %s", cudaGetErrorString(e));
+    delete h;
+    return DIS_ERR_CUDA;
+  }
+  rc = plan(h, max_w, max_h);
+  if (rc != DIS_OK) {
+    g_create_error = h->err;
+    dis_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return DIS_OK;
+}
+
+int dis_destroy(dis_handle* h) {
+  if (!h) return DIS_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  drop_graph(h);
+  if (h->slab) cudaFree(h->slab);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return DIS_OK;
+}
+
+int dis_set_params(dis_handle* h, const dis_params* params) {
+  if (!h) return DIS_ERR_INVALID_ARG;
+  char why[128];
+  int rc = dis_params_validate(params, why, sizeof why);
+  if (rc != DIS_OK) return fail(h, rc, "invalid parameters: %s", why);
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaStreamSynchronize(h->stream));
+  h->P = *params;
+  derive_opt(h->P, &h->opt);
+  const int w = h->w_org, hh = h->h_org;
+  h->lv.clear();
+  h->w_org = h->h_org = 0;
+  return plan(h, w, hh);
+}
+
+void* dis_stream(dis_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+int dis_enable_stage_timing(dis_handle* h, int on) {
+  if (!h) return DIS_ERR_INVALID_ARG;
+  h->stage_timing = on != 0;
+  return DIS_OK;
+}
+
+int dis_enable_taps(dis_handle* h, int on) {
+  if (!h) return DIS_ERR_INVALID_ARG;
+  h->taps = on != 0;
+  if (!on) h->tapdata.clear();
+  return DIS_OK;
+}
+
+int dis_fetch_tap(dis_handle* h, int tap, int level, float* out, size_t n_floats, size_t* n_written) {
+  if (!h || tap < 0 || level < 0) return DIS_ERR_INVALID_ARG;
+  if (tap >= (int)h->tapdata.size() || level >= (int)h->tapdata[tap].size() ||
+      h->tapdata[tap][level].data.empty())
+    return fail(h, DIS_ERR_INVALID_ARG, "tap %d level %d not recorded", tap, level);
+  const auto& v = h->tapdata[tap][level].data;
+  if (n_written) *n_written = v.size();
+  if (out) {
+    if (n_floats < v.size()) return fail(h, DIS_ERR_INVALID_ARG, "tap buffer too small");
+    memcpy(out, v.data(), v.size() * sizeof(float));
+  }
+  return DIS_OK;
+}
+
+int dis_get_timings(dis_handle* h, dis_timings* out) {
+  if (!h || !out) return DIS_ERR_INVALID_ARG;
+  *out = h->tm;
+  return DIS_OK;
+}
+
+int dis_host_alloc(void** ptr, size_t bytes) {
+  if (!ptr) return DIS_ERR_INVALID_ARG;
+  return cudaHostAlloc(ptr, bytes, cudaHostAllocDefault) == cudaSuccess ? DIS_OK : DIS_ERR_NOMEM;
+}
+int dis_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? DIS_OK : DIS_ERR_CUDA; }
+
+int dis_submit_u8_device(dis_handle* h, const uint8_t* d_a, const uint8_t* d_b, int w, int h_img, int pitch,
+                         float* d_flow) {
+  if (!h || !d_a || !d_b || !d_flow || pitch < w) return h ? fail(h, DIS_ERR_INVALID_ARG, "bad argument") : DIS_ERR_INVALID_ARG;
+  CU(h, cudaSetDevice(h->device));
+  int rc = plan(h, w, h_img);
+  if (rc != DIS_OK) return rc;
+  reset_timings(h);
+  rc = enqueue_run_device(h, d_a, d_b, pitch, reinterpret_cast<float2*>(d_flow));
+  h->in_flight = rc == DIS_OK;
+  return rc;
+}
+
+int dis_submit_u8(dis_handle* h, const uint8_t* a, const uint8_t* b, int w, int h_img, int pitch, float* flow_out) {
+  if (!h || !a || !b || !flow_out || pitch < w) return h ? fail(h, DIS_ERR_INVALID_ARG, "bad argument") : DIS_ERR_INVALID_ARG;
+  CU(h, cudaSetDevice(h->device));
+  int rc = plan(h, w, h_img);
+  if (rc != DIS_OK) return rc;
+  reset_timings(h);
+  CU(h, cudaEventCreate(&h->ev[0]));
+  CU(h, cudaEventCreate(&h->ev[1]));
+  CU(h, cudaEventCreate(&h->ev[2]));
+  CU(h, cudaEventCreate(&h->ev[3]));
+  CU(h, cudaEventRecord(h->ev[0], h->stream));
+  CU(h, cudaMemcpy2DAsync(h->d_a, w, a, pitch, w, h_img, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpy2DAsync(h->d_b, w, b, pitch, w, h_img, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaEventRecord(h->ev[1], h->stream));
+  rc = enqueue_run_device(h, h->d_a, h->d_b, w, h->d_out);
+  if (rc != DIS_OK) return rc;
+  CU(h, cudaEventRecord(h->ev[2], h->stream));
+  CU(h, cudaMemcpyAsync(flow_out, h->d_out, sizeof(float2) * (size_t)w * h_img, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaEventRecord(h->ev[3], h->stream));
+  h->in_flight = true;
+  return DIS_OK;
+}
+
+int dis_wait(dis_handle* h) {
+  if (!h) return DIS_ERR_INVALID_ARG;
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaStreamSynchronize(h->stream));
+  if (h->ev[0]) {
+    cudaEventElapsedTime(&h->tm.h2d_ms, h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&h->tm.d2h_ms, h->ev[2], h->ev[3]);
+    cudaEventElapsedTime(&h->tm.total_ms, h->ev[0], h->ev[3]);
+    for (int i = 0; i < 4; ++i) {
+      cudaEventDestroy(h->ev[i]);
+      h->ev[i] = nullptr;
+    }
+    if (h->P.verbosity > 0)  // format of kroeger/oflow.cpp:359
+      printf("TIME (O.Flow Run-Time   ) (ms): %3g\n", h->tm.total_ms - h->tm.h2d_ms - h->tm.d2h_ms);
+  }
+  h->in_flight = false;
+  CU(h, cudaGetLastError());
+  return DIS_OK;
+}
+
+int dis_run_u8(dis_handle* h, const uint8_t* a, const uint8_t* b, int w, int h_img, int pitch, float* flow_out) {
+  int rc = dis_submit_u8(h, a, b, w, h_img, pitch, flow_out);
+  if (rc != DIS_OK) return rc;
+  return dis_wait(h);
+}
+
+int dis_fetch_level_flow(dis_handle* h, float* out, size_t n_floats) {
+  if (!h || !out || h->lv.empty()) return DIS_ERR_INVALID_ARG;
+  const LevelBufs& L = h->lv[h->P.lv_l];
+  const size_t n = (size_t)L.g.w * L.g.h * 2;
+  if (n_floats < n) return fail(h, DIS_ERR_INVALID_ARG, "buffer too small: need %zu floats", n);
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaMemcpyAsync(out, L.flow, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return DIS_OK;
+}
+
+int dis_run_pyramids(dis_handle* h, const float* const* im_ao, const float* const* im_ao_dx,
+                     const float* const* im_ao_dy, const float* const* im_bo, const float* const* im_bo_dx,
+                     const float* const* im_bo_dy, int imgpadding, int width, int height, const float* initflow,
+                     float* outflow) {
+  if (!h || !im_ao || !im_ao_dx || !im_ao_dy || !im_bo || !outflow)
+    return h ? fail(h, DIS_ERR_INVALID_ARG, "null pyramid/outflow pointer") : DIS_ERR_INVALID_ARG;
+  const dis_params& q = h->P;
+  if (imgpadding != q.patchsz)
+    return fail(h, DIS_ERR_UNSUPPORTED, "imgpadding (%d) must equal patchsz (%d) as in kroeger/run_dense.cpp:393",
+                imgpadding, q.patchsz);
+  const int sc = 1 << q.lv_f;
+  if (width <= 0 || height <= 0 || width % sc || height % sc)
+    return fail(h, DIS_ERR_INVALID_ARG, "width/height must be positive multiples of 2^lv_f (kroeger/oflow.h:87)");
+  CU(h, cudaSetDevice(h->device));
+  int rc = plan(h, width, height);  // already padded: plan() adds no further padding
+  if (rc != DIS_OK) return rc;
+  reset_timings(h);
+  h->launches = 0;
+  cudaEvent_t e0, e1, e2, e3;
+  CU(h, cudaEventCreate(&e0));
+  CU(h, cudaEventCreate(&e1));
+  CU(h, cudaEventCreate(&e2));
+  CU(h, cudaEventCreate(&e3));
+  CU(h, cudaEventRecord(e0, h->stream));
+  for (int l = q.lv_l; l <= q.lv_f; ++l) {
+    LevelBufs& L = h->lv[l];
+    const float* src[6] = {im_ao[l], im_ao_dx[l], im_ao_dy[l], im_bo[l], im_bo_dx ? im_bo_dx[l] : nullptr,
+                           im_bo_dy ? im_bo_dy[l] : nullptr};
+    float* dst[6] = {L.Ia, L.Iax, L.Iay, L.Ib, L.Ibx, L.Iby};
+    for (int k = 0; k < 6; ++k) {
+      if (!dst[k]) continue;
+      if (!src[k]) return fail(h, DIS_ERR_INVALID_ARG, "pyramid %d level %d is null", k, l);
+      CU(h, cudaMemcpy2DAsync(dst[k], sizeof(float) * L.g.pitch, src[k], sizeof(float) * L.g.tw,
+                              sizeof(float) * L.g.tw, L.g.th, cudaMemcpyHostToDevice, h->stream));
+    }
+  }
+  float2* d_init = nullptr;
+  if (initflow) {  // resolution of level lv_f+1 (kroeger/oflow.h:91); staged in the output buffer
+    const LevelGeom& gc = h->lv[q.lv_f].g;
+    const size_t n = (size_t)(gc.w / 2) * (gc.h / 2);
+    d_init = h->d_out;
+    CU(h, cudaMemcpyAsync(d_init, initflow, n * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+  }
+  CU(h, cudaEventRecord(e1, h->stream));
+  rc = enqueue_engine(h, d_init);
+  if (rc != DIS_OK) return rc;
+  CU(h, cudaEventRecord(e2, h->stream));
+  const LevelBufs& L = h->lv[q.lv_l];
+  CU(h, cudaMemcpyAsync(outflow, L.flow, sizeof(float2) * (size_t)L.g.w * L.g.h, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaEventRecord(e3, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  cudaEventElapsedTime(&h->tm.h2d_ms, e0, e1);
+  cudaEventElapsedTime(&h->tm.d2h_ms, e2, e3);
+  cudaEventElapsedTime(&h->tm.total_ms, e0, e3);
+  h->tm.launches = h->launches;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaEventDestroy(e2);
+  cudaEventDestroy(e3);
+  if (q.verbosity > 0) printf("TIME (O.Flow Run-Time   ) (ms): %3g\n", h->tm.total_ms);
+  CU(h, cudaGetLastError());
+  return DIS_OK;
+}
+
+int dis_write_flo(const char* path, const float* flow_uv, int w, int h) {
+  if (!path || !flow_uv || w <= 0 || h <= 0) return DIS_ERR_INVALID_ARG;
+  FILE* f = fopen(path, "wb");
+  if (!f) return DIS_ERR_IO;
+  int ok = fwrite("PIEH", 1, 4, f) == 4;  // kroeger/run_dense.cpp:28-31
+  ok = ok && fwrite(&w, sizeof(int), 1, f) == 1 && fwrite(&h, sizeof(int), 1, f) == 1;
+  ok = ok && fwrite(flow_uv, sizeof(float), (size_t)2 * w * h, f) == (size_t)2 * w * h;
+  ok = (fclose(f) == 0) && ok;
+  return ok ? DIS_OK : DIS_ERR_IO;
+}
+
+int dis_read_flo(const char* path, float* flow_uv, size_t n_floats, int* w, int* h) {
+  if (!path || !w || !h) return DIS_ERR_INVALID_ARG;
+  FILE* f = fopen(path, "rb");
+  if (!f) return DIS_ERR_IO;
+  float tag = 0;
+  int rc = DIS_OK;
+  if (fread(&tag, sizeof(float), 1, f) != 1 || tag != 202021.25f ||  // flow_code/C/flowIO.cpp:27,66-72
+      fread(w, sizeof(int), 1, f) != 1 || fread(h, sizeof(int), 1, f) != 1 || *w < 1 || *h < 1 || *w > 99999 ||
+      *h > 99999)
+    rc = DIS_ERR_IO;
+  if (rc == DIS_OK && flow_uv) {
+    const size_t n = (size_t)2 * *w * *h;
+    if (n_floats < n)
+      rc = DIS_ERR_INVALID_ARG;
+    else if (fread(flow_uv, sizeof(float), n, f) != n)
+      rc = DIS_ERR_IO;
+  }
+  fclose(f);
+  return rc;
+}
+
+}  // extern "C"

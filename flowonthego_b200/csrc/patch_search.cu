@@ -1,0 +1,270 @@
+// patch_search.cu -- stage 2: per-patch inverse-compositional Gauss-Newton search.
+//
+// Replaces, for one pyramid level, PatGridClass::InitializeGrid / SetTargetImage /
+// InitializeFromCoarserOF / Optimize (kroeger/patchgrid.cpp:98-141, 195-211) and everything in
+// PatClass underneath (kroeger/patch.cpp): template + gradient extraction (:287-332), Hessian
+// (:71-88), OptimizeStart/OptimizeIter (:120-212), bilinear patch sampling (:335-402), the
+// L2/L1/pseudo-Huber error image (:223-262) and the termination test (:264-284).
+//
+// Mapping: 8 lanes ("octet") per patch, 4 patches per warp.  Lane c of the octet owns exactly
+// the elements e = 8i + c of the row-major p x p patch -- i.e. one of the 8 accumulator chains
+// of Eigen 3.3's SSE reduction (two 4-wide packets, Eigen/src/Core/Redux.h) -- so the per-patch
+// sums are formed in the reference's float order: each lane adds its chain sequentially in
+// registers, then the 8 partial sums are combined with three xor-shuffles as
+// (p0+p1) [+ tail packet] -> (r0+r2)+(r1+r3).  Template, both gradient patches and the current
+// residual live in registers; the only memory traffic in the iteration loop is the 4 bilinear
+// taps per element of the target image.  No FMA (-fmad=false), IEEE div/sqrt.
+#include "common.cuh"
+
+namespace dis {
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// Combine the 8 chain sums of an octet in Eigen order.  `extra` is the element of the trailing
+// 4-wide packet (only when n % 8 == 4; held by lanes c < 4).
+template <bool HAS_EXTRA>
+__device__ __forceinline__ float octet_reduce(float chain, float extra) {
+  float r = chain + __shfl_xor_sync(FULL, chain, 4);  // p0[k] + p1[k]
+  if (HAS_EXTRA) r = r + extra;                       // p0 += packet(alignedEnd2)
+  const float t = r + __shfl_xor_sync(FULL, r, 2);    // r0+r2 | r1+r3
+  const float s = t + __shfl_xor_sync(FULL, t, 1);    // (r0+r2)+(r1+r3)
+  return __shfl_sync(FULL, s, 0, 8);
+}
+
+template <int P>
+__global__ void __launch_bounds__(128) k_patch_search(const PatchSearchArgs a) {
+  constexpr int N = P * P;
+  constexpr int NI = N / 8;             // chain length
+  constexpr bool EX = (N % 8) == 4;     // trailing packet present
+  constexpr int NE = NI + (EX ? 1 : 0);
+  constexpr int LB = -P / 2;
+
+  const int c = threadIdx.x & 7;
+  int ip = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const bool live = ip < a.g.nop;
+  if (!live) ip = a.g.nop - 1;  // dead octets shadow the last patch (shuffles stay warp-uniform)
+
+  const int pitch = a.g.pitch, pad = a.g.pad;
+  const int gx = ip / a.g.noph, gy = ip - gx * a.g.noph;
+  const int cx = gx * a.o.steps + a.g.offw, cy = gy * a.o.steps + a.g.offh;
+
+  // element offsets of this lane inside a patch window (row-major p x p)
+  int off[NE];
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const int e = 8 * i + c;
+    off[i] = (e / P) * pitch + (e % P);
+  }
+  if (EX) {
+    const int e = 8 * NI + (c & 3);
+    off[NE - 1] = (e / P) * pitch + (e % P);
+  }
+  const bool exl = c < 4;  // lanes holding a real tail element
+
+  // ---- InitializePatch: template and gradients at the integer patch centre (patch.cpp:287-332)
+  float T[NE], GX[NE], GY[NE];
+  {
+    const size_t base = (size_t)(cy + pad + LB) * pitch + (cx + pad + LB);
+#pragma unroll
+    for (int i = 0; i < NE; ++i) {
+      T[i] = __ldg(a.I0 + base + off[i]);
+      GX[i] = __ldg(a.I0x + base + off[i]);
+      GY[i] = __ldg(a.I0y + base + off[i]);
+    }
+  }
+  if (a.o.patnorm > 0) {
+    float ch = T[0];
+#pragma unroll
+    for (int i = 1; i < NI; ++i) ch = ch + T[i];
+    const float m = octet_reduce<EX>(ch, EX ? T[NE - 1] : 0.0f) / (float)N;
+#pragma unroll
+    for (int i = 0; i < NE; ++i) T[i] = T[i] - m;
+  }
+  // ---- ComputeHessian (patch.cpp:71-88)
+  float H00, H01, H11;
+  {
+    float c0 = GX[0] * GX[0], c1 = GX[0] * GY[0], c2 = GY[0] * GY[0];
+#pragma unroll
+    for (int i = 1; i < NI; ++i) {
+      c0 = c0 + GX[i] * GX[i];
+      c1 = c1 + GX[i] * GY[i];
+      c2 = c2 + GY[i] * GY[i];
+    }
+    H00 = octet_reduce<EX>(c0, EX ? GX[NE - 1] * GX[NE - 1] : 0.0f);
+    H01 = octet_reduce<EX>(c1, EX ? GX[NE - 1] * GY[NE - 1] : 0.0f);
+    H11 = octet_reduce<EX>(c2, EX ? GY[NE - 1] * GY[NE - 1] : 0.0f);
+    if (H00 * H11 - H01 * H01 == 0.0f) {
+      H00 = (float)((double)H00 + 1e-10);
+      H11 = (float)((double)H11 + 1e-10);
+    }
+  }
+  // LLT factor of H (Eigen LLT unblocked, early exit on a non-positive pivot); H is constant per
+  // patch so the factor is hoisted out of the iteration loop (same values every iteration).
+  float L00 = H00, L10 = H01, L11 = H11;
+  {
+    float x = L00;
+    if (!(x <= 0.0f)) {
+      L00 = x = sqrtf(x);
+      L10 = L10 / x;
+      x = L11 - L10 * L10;
+      if (!(x <= 0.0f)) L11 = sqrtf(x);
+    }
+  }
+
+  // ---- InitializeFromCoarserOF (patchgrid.cpp:195-211)
+  float pinx = 0.0f, piny = 0.0f;
+  if (a.flow_coarse != nullptr) {
+    const int x = (int)floorf((float)cx / 2), y = (int)floorf((float)cy / 2);
+    const float2 f = __ldg(a.flow_coarse + (size_t)y * (a.g.w / 2) + x);
+    pinx = f.x * 2;
+    piny = f.y * 2;
+  }
+
+  // ---- OptimizeStart (patch.cpp:120-156)
+  float px = pinx, py = piny;
+  float ptx = (float)cx + px, pty = (float)cy + py;
+  const float stx = ptx, sty = pty;
+  float dpx = 0.0f, dpy = 0.0f;
+  float dp_sq_init = 1e-10f, mares = 1e5f;
+  int cnt = 0;
+  const bool oob_start = ptx < a.g.lb || pty < a.g.lb || ptx > a.g.ubw || pty > a.g.ubh;
+  bool conv = oob_start;
+  if (oob_start) {  // sample somewhere legal; the result is discarded
+    ptx = (float)cx;
+    pty = (float)cy;
+  }
+
+  float R[NE];   // |residual| per element (pweight)
+  float bx = 0.0f, by = 0.0f;
+  bool first = true;
+  while (true) {
+    if (!first) {
+      if (!__any_sync(FULL, !conv)) break;
+      if (!conv) {
+        // ---- OptimizeIter body (patch.cpp:172-208)
+        cnt++;
+        // delta_p = Hes.llt().solve(delta_p)
+        float y0 = bx / L00;
+        float y1 = by - L10 * y0;
+        y1 = y1 / L11;
+        const float x1 = y1 / L11;
+        float x0 = y0 - L10 * x1;
+        x0 = x0 / L00;
+        dpx = x0;
+        dpy = x1;
+        px = px - dpx;
+        py = py - dpy;
+        ptx = (float)cx + px;
+        pty = (float)cy + py;
+        const float ox = stx - ptx, oy = sty - pty;
+        if (sqrtf(ox * ox + oy * oy) > a.o.outlierthresh || ptx < a.g.lb || pty < a.g.lb ||
+            ptx > a.g.ubw || pty > a.g.ubh) {
+          px = pinx;
+          py = piny;
+          ptx = (float)cx + px;
+          pty = (float)cy + py;
+          conv = true;  // error image is still recomputed below (patch.cpp:210)
+        }
+      }
+    }
+    // ---- OptimizeComputeErrImg (patch.cpp:264-284); converged octets recompute identical values
+    {
+      // getPatchStaticBil (patch.cpp:335-402)
+      const int posx = (int)ceilf(ptx + .00001f), posy = (int)ceilf(pty + .00001f);
+      const float rx = ptx - (float)(int)floorf(ptx), ry = pty - (float)(int)floorf(pty);
+      const float w0 = rx * ry, w1 = (1 - rx) * ry, w2 = rx * (1 - ry), w3 = (1 - rx) * (1 - ry);
+      const float* base = a.I1 + (size_t)(posy + pad + LB) * pitch + (posx + pad + LB);
+      float ch = 0.0f;
+#pragma unroll
+      for (int i = 0; i < NE; ++i) {
+        const float* q = base + off[i];
+        const float va = __ldg(q), vb = __ldg(q - 1), vc = __ldg(q - pitch), vd = __ldg(q - pitch - 1);
+        R[i] = w0 * va + w1 * vb + w2 * vc + w3 * vd;
+        if (i == 0)
+          ch = R[0];
+        else if (i < NI)
+          ch = ch + R[i];
+      }
+      float m = 0.0f;
+      if (a.o.patnorm > 0) m = octet_reduce<EX>(ch, EX ? R[NE - 1] : 0.0f) / (float)N;
+      // LossComputeErrorImage (patch.cpp:223-262) fused with the projections of the next
+      // iteration (patch.cpp:178-179) and the L1 norm of the weights (:278)
+      float cgx = 0.0f, cgy = 0.0f, cab = 0.0f;
+      float egx = 0.0f, egy = 0.0f, eab = 0.0f;
+#pragma unroll
+      for (int i = 0; i < NE; ++i) {
+        float d = R[i];
+        if (a.o.patnorm > 0) d = d - m;
+        d = d - T[i];
+        if (a.o.costfct == 1) {
+          d = copysignf(sqrtf(fabsf(d)), d);
+        } else if (a.o.costfct == 2) {
+          d = copysignf(sqrtf((sqrtf(1.0f + (d * d) / 25.0f) - 1.0f) * 50.0f), d);
+        }
+        const float ad = fabsf(d);
+        R[i] = ad;
+        const float tx = GX[i] * d, ty = GY[i] * d;
+        if (i == 0) {
+          cgx = tx; cgy = ty; cab = ad;
+        } else if (i < NI) {
+          cgx = cgx + tx; cgy = cgy + ty; cab = cab + ad;
+        } else {
+          egx = tx; egy = ty; eab = ad;
+        }
+      }
+      const float nbx = octet_reduce<EX>(cgx, egx);
+      const float nby = octet_reduce<EX>(cgy, egy);
+      const float asum = octet_reduce<EX>(cab, eab);
+      if (!conv || (first && !oob_start)) {
+        bx = nbx;
+        by = nby;
+      }
+      if (first ? !oob_start : true) {
+        // state update + termination test; harmless for octets that are already converged
+        // because nothing below is read again once conv is set.
+        const float dp_sq = dpx * dpx + dpy * dpy;
+        if (cnt == 1) dp_sq_init = dp_sq;
+        if (!conv) {
+          const float mares_old = mares;
+          mares = asum / (float)N;
+          if (!((cnt < a.o.max_iter) & (mares > a.o.res_thresh) &
+                ((cnt < a.o.min_iter) | (dp_sq / dp_sq_init >= a.o.dp_thresh)) &
+                ((cnt < a.o.min_iter) | (mares / mares_old <= a.o.dr_thresh))))
+            conv = true;
+        }
+      }
+    }
+    first = false;
+  }
+  (void)exl;
+
+  // ---- results: p_iter and the weight patch (read by AggregateFlowDense)
+  if (live) {
+    if (c == 0) a.pflow[ip] = make_float2(px, py);
+    float* pw = a.pweight + (size_t)ip * N;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) pw[8 * i + c] = oob_start ? 0.0f : R[i];
+    if (EX && c < 4) pw[8 * NI + c] = oob_start ? 0.0f : R[NE - 1];
+  }
+}
+
+}  // namespace
+
+int launch_patch_search(const PatchSearchArgs& a, cudaStream_t st) {
+  const int threads = 128;
+  const int blocks = (a.g.nop * 8 + threads - 1) / threads;
+  switch (a.o.p) {
+    case 4: k_patch_search<4><<<blocks, threads, 0, st>>>(a); break;
+    case 6: k_patch_search<6><<<blocks, threads, 0, st>>>(a); break;
+    case 8: k_patch_search<8><<<blocks, threads, 0, st>>>(a); break;
+    case 10: k_patch_search<10><<<blocks, threads, 0, st>>>(a); break;
+    case 12: k_patch_search<12><<<blocks, threads, 0, st>>>(a); break;
+    case 14: k_patch_search<14><<<blocks, threads, 0, st>>>(a); break;
+    case 16: k_patch_search<16><<<blocks, threads, 0, st>>>(a); break;
+    default: return 1;
+  }
+  return 0;
+}
+
+}  // namespace dis
