@@ -75,6 +75,11 @@ class Timings(ctypes.Structure):
                                                "varref_ms", "finish_ms", "d2h_ms")] + [("launches", ctypes.c_int32)]
 
 
+class KernelTime(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char * 32), ("level", ctypes.c_int32), ("launches", ctypes.c_int32),
+                ("ms", ctypes.c_float), ("alg_bytes", ctypes.c_double)]
+
+
 def lib():
     """Loads libdis_b200.so; raises if it has not been built (no fallback of any kind)."""
     global _LIB
@@ -109,6 +114,8 @@ def lib():
         L.dis_enable_stage_timing.argtypes = [vp, ip]
         L.dis_enable_taps.argtypes = [vp, ip]
         L.dis_fetch_tap.argtypes = [vp, ip, ip, fp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
+        L.dis_enable_kernel_profile.argtypes = [vp, ip]
+        L.dis_get_kernel_profile.argtypes = [vp, ctypes.POINTER(KernelTime), ip, ctypes.POINTER(ip)]
         L.dis_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
         L.dis_host_free.argtypes = [vp]
         L.dis_write_flo.argtypes = [ctypes.c_char_p, fp, ip, ip]
@@ -255,6 +262,18 @@ class Engine:
         out = np.empty(n.value, np.float32)
         _check(lib().dis_fetch_tap(self._h, which, level, _as_fp(out), out.size, ctypes.byref(n)), self._h)
         return out
+
+    def enable_kernel_profile(self, on=True):
+        _check(lib().dis_enable_kernel_profile(self._h, int(on)), self._h)
+
+    def kernel_profile(self):
+        """[{name, level, launches, ms, alg_bytes}] accumulated since enable_kernel_profile(True)."""
+        n = ctypes.c_int()
+        _check(lib().dis_get_kernel_profile(self._h, None, 0, ctypes.byref(n)), self._h)
+        arr = (KernelTime * max(n.value, 1))()
+        _check(lib().dis_get_kernel_profile(self._h, arr, n.value, ctypes.byref(n)), self._h)
+        return [dict(name=arr[i].name.decode(), level=arr[i].level, launches=arr[i].launches, ms=arr[i].ms,
+                     alg_bytes=arr[i].alg_bytes) for i in range(n.value)]
 
     def timings(self):
         t = Timings()

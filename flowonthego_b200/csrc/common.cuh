@@ -33,9 +33,31 @@ struct VarParams {  // kroeger/refine_variational.cpp:28-42
   int n_inner, n_solver;
 };
 
+// Optional per-kernel profiling hook (CUDA events around every launch; used by bench.py's roofline
+// leg through dis_profile_kernels, never on the timed path).
+struct Prof {
+  virtual void begin(const char* kernel, int level, double alg_bytes) = 0;
+  virtual void end() = 0;
+};
+struct ProfScope {
+  Prof* p;
+  ProfScope(Prof* p_, const char* k, int level, double bytes) : p(p_) { if (p) p->begin(k, level, bytes); }
+  ~ProfScope() { if (p) p->end(); }
+};
+
+// Per-run pointers live in a small device-side mailbox so that the recorded CUDA graph does not
+// depend on the caller's buffers: a one-thread kernel refreshes it before every graph launch.
+struct Mailbox {
+  const uint8_t* a;
+  const uint8_t* b;
+  float2* out;
+  int pitch;  // row pitch of a and b in bytes
+};
+void launch_set_mailbox(Mailbox* mb, const uint8_t* a, const uint8_t* b, float2* out, int pitch, cudaStream_t st);
+
 // ---- launchers (defined in the .cu files) --------------------------------------------------
 // pyramid.cu
-void launch_level0(const uint8_t* src_a, const uint8_t* src_b, int w_org, int h_org, int src_pitch,
+void launch_level0(const Mailbox* mb, int w_org, int h_org,
                    int left, int top, const LevelGeom& g, float* Ia, float* Iax, float* Iay,
                    float* Ib, float* Ibx, float* Iby, cudaStream_t st);
 void launch_downsample(const LevelGeom& gf, const LevelGeom& gc, const float* Ia_f, const float* Ib_f,
@@ -70,10 +92,10 @@ struct VarRefBuffers {
   int* progress;                                                   // SOR wavefront flags
 };
 int launch_varref(const LevelGeom& g, const VarParams& v, const float* I0, const float* I1,
-                  float2* flow, const VarRefBuffers& b, cudaStream_t st);
+                  float2* flow, const VarRefBuffers& b, cudaStream_t st, Prof* prof = nullptr);
 size_t varref_progress_ints(int h, int n_solver);
 // finish.cu
 void launch_finish(const float2* flow_l, int wl, int hl, int lv_l, int left, int top, int w_org,
-                   int h_org, float2* out, cudaStream_t st);
+                   int h_org, const Mailbox* mb, cudaStream_t st);
 
 }  // namespace dis

@@ -38,6 +38,43 @@ struct Tap {
   std::vector<float> data;
 };
 
+struct KernelProf : Prof {
+  cudaStream_t st = nullptr;
+  std::vector<dis_kernel_time> recs;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  dis_kernel_time* cur = nullptr;
+  void begin(const char* kernel, int level, double bytes) override {
+    if (!e0) {
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+    }
+    cur = nullptr;
+    for (auto& r : recs)
+      if (r.level == level && strcmp(r.name, kernel) == 0) cur = &r;
+    if (!cur) {
+      dis_kernel_time r{};
+      snprintf(r.name, sizeof r.name, "%s", kernel);
+      r.level = level;
+      recs.push_back(r);
+      cur = &recs.back();
+    }
+    cur->launches++;
+    cur->alg_bytes += bytes;
+    cudaEventRecord(e0, st);
+  }
+  void end() override {
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (cur) cur->ms += ms;
+  }
+  ~KernelProf() {
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+  }
+};
+
 }  // namespace
 
 struct dis_handle {
@@ -56,6 +93,7 @@ struct dis_handle {
   float *pweight = nullptr, *pweight_bw = nullptr;
   VarRefBuffers vb{};
   float2* d_out = nullptr;
+  Mailbox* mailbox = nullptr;
   char* slab = nullptr;
   size_t slab_bytes = 0;
 
@@ -63,11 +101,12 @@ struct dis_handle {
   bool use_graph = true;
   cudaGraphExec_t graph_exec = nullptr;
   int graph_w = 0, graph_h = 0;
-  const void *graph_a = nullptr, *graph_b = nullptr, *graph_out = nullptr;
 
   // timing / taps
   bool stage_timing = false;
   bool taps = false;
+  bool kprof_on = false;
+  KernelProf kprof;
   std::vector<std::vector<Tap>> tapdata;  // [tap][level]
   dis_timings tm{};
   cudaEvent_t ev[10] = {};
@@ -195,7 +234,9 @@ size_t carve(dis_handle* h, int w, int h_img, char* base, bool assign) {
     vb.progress = c.take<int>(varref_progress_ints(gf.h, std::max(1, q.tv_solverit)));
   }
   float2* d_out = c.take<float2>((size_t)w * h_img);
+  Mailbox* mailbox = c.take<Mailbox>(1);
   if (assign) {
+    h->mailbox = mailbox;
     h->lv = lv;
     h->d_a = d_a;
     h->d_b = d_b;
@@ -268,12 +309,16 @@ void tap_image(dis_handle* h, int tap, int level, const float* d, const LevelGeo
 }
 
 // stage 1 (kroeger/run_dense.cpp:298-344): pyramids of both frames from the u8 inputs
-int enqueue_pyramids(dis_handle* h, const uint8_t* d_a, const uint8_t* d_b, int src_pitch) {
+int enqueue_pyramids(dis_handle* h) {
   const dis_params& q = h->P;
   for (int l = 0; l <= q.lv_f; ++l) {
     LevelBufs& L = h->lv[l];
+    // SURVEY 8(d) B_P: u8 in (level 0 only), I of both frames out, Ix/Iy of frame a on used levels
+    const double np_ = (double)L.g.tw * L.g.th;
+    ProfScope ps(h->kprof_on ? &h->kprof : nullptr, l == 0 ? "k_pyr_level0" : "k_pyr_down", l,
+                 (l == 0 ? 2.0 * h->w_org * h->h_org : 0.0) + 8.0 * np_ + (l >= q.lv_l ? 8.0 * np_ : 0.0));
     if (l == 0)
-      launch_level0(d_a, d_b, h->w_org, h->h_org, src_pitch, h->left, h->top, L.g, L.Ia, L.Iax, L.Iay, L.Ib,
+      launch_level0(h->mailbox, h->w_org, h->h_org, h->left, h->top, L.g, L.Ia, L.Iax, L.Iay, L.Ib,
                     L.Ibx, L.Iby, h->stream);
     else
       launch_downsample(h->lv[l - 1].g, L.g, h->lv[l - 1].Ia, h->lv[l - 1].Ib, L.Ia, L.Iax, L.Iay, L.Ib,
@@ -330,6 +375,7 @@ int enqueue_engine(dis_handle* h, const float2* d_initflow) {
   vp.hd = q.tv_delta * 0.5f / 3.0f;
   vp.omega = q.tv_sor;
   vp.n_solver = q.tv_solverit;
+  Prof* prof = h->kprof_on ? &h->kprof : nullptr;
   for (int sl = q.lv_f; sl >= q.lv_l; --sl) {
     LevelBufs& L = h->lv[sl];
     float t_search = 0, t_dens = 0, t_var = 0;
@@ -341,6 +387,10 @@ int enqueue_engine(dis_handle* h, const float2* d_initflow) {
     {
       StageClock ck(h, &h->tm.search_ms);
       PatchSearchArgs pa{L.Ia, L.Iax, L.Iay, L.Ib, L.g, h->opt, coarse, h->pflow, h->pweight};
+      // SURVEY 8(d) B_D: 4 padded arrays in, coarse flow in, patch results out
+      const double np_ = (double)L.g.tw * L.g.th;
+      ProfScope ps(prof, "k_patch_search", sl,
+                   16.0 * np_ + (sl < q.lv_f ? 8.0 * (double)(L.g.w / 2) * (L.g.h / 2) : 0.0) + 16.0 * L.g.nop);
       if (launch_patch_search(pa, h->stream)) return fail(h, DIS_ERR_UNSUPPORTED, "patch size %d", h->opt.p);
       h->launches++;
       t_search = ck.stop();
@@ -349,6 +399,8 @@ int enqueue_engine(dis_handle* h, const float2* d_initflow) {
     {
       StageClock ck(h, &h->tm.densify_ms);
       DensifyArgs da{L.g, h->opt, h->pflow, h->pweight, nullptr, nullptr, L.flow};
+      // SURVEY 8(d) B_A: patch results + I0,I1 in, flow out
+      ProfScope ps(prof, "k_densify", sl, 16.0 * L.g.nop + 8.0 * (double)L.g.tw * L.g.th + 8.0 * (double)L.g.w * L.g.h);
       launch_densify(da, h->stream);
       h->launches++;
       t_dens = ck.stop();
@@ -357,7 +409,7 @@ int enqueue_engine(dis_handle* h, const float2* d_initflow) {
     if (q.usetvref) {
       StageClock ck(h, &h->tm.varref_ms);
       vp.n_inner = q.tv_innerit * (sl + 1);  // refine_variational.cpp:36
-      const int n = launch_varref(L.g, vp, L.Ia, L.Ib, L.flow, h->vb, h->stream);
+      const int n = launch_varref(L.g, vp, L.Ia, L.Ib, L.flow, h->vb, h->stream, prof);
       if (n < 0) return fail(h, DIS_ERR_UNSUPPORTED, "level %d (%dx%d) too small for refinement", sl, L.g.w, L.g.h);
       h->launches += n;
       t_var = ck.stop();
@@ -371,9 +423,11 @@ int enqueue_engine(dis_handle* h, const float2* d_initflow) {
   return DIS_OK;
 }
 
-int enqueue_finish(dis_handle* h, float2* d_out) {
+int enqueue_finish(dis_handle* h) {
   const LevelBufs& L = h->lv[h->P.lv_l];
-  launch_finish(L.flow, L.g.w, L.g.h, h->P.lv_l, h->left, h->top, h->w_org, h->h_org, d_out, h->stream);
+  ProfScope ps(h->kprof_on ? &h->kprof : nullptr, "k_finish", h->P.lv_l,
+               8.0 * (double)L.g.w * L.g.h + 8.0 * (double)h->w_org * h->h_org);
+  launch_finish(L.flow, L.g.w, L.g.h, h->P.lv_l, h->left, h->top, h->w_org, h->h_org, h->mailbox, h->stream);
   h->launches++;
   CU(h, cudaGetLastError());
   return DIS_OK;
@@ -381,19 +435,19 @@ int enqueue_finish(dis_handle* h, float2* d_out) {
 
 // Enqueue the whole device-side run (stage 1 .. finish); replayed from a CUDA graph when possible.
 int enqueue_run_device(dis_handle* h, const uint8_t* d_a, const uint8_t* d_b, int pitch, float2* d_out) {
-  const bool graphable = h->use_graph && !h->taps && !h->stage_timing;
-  if (graphable && h->graph_exec && h->graph_a == d_a && h->graph_b == d_b && h->graph_out == d_out &&
-      h->graph_w == h->w_org && h->graph_h == h->h_org) {
+  launch_set_mailbox(h->mailbox, d_a, d_b, d_out, pitch, h->stream);
+  const bool graphable = h->use_graph && !h->taps && !h->stage_timing && !h->kprof_on;
+  if (graphable && h->graph_exec && h->graph_w == h->w_org && h->graph_h == h->h_org) {
     CU(h, cudaGraphLaunch(h->graph_exec, h->stream));
     return DIS_OK;
   }
   if (graphable) {
     drop_graph(h);
-    h->launches = 0;
+    h->launches = 1;
     CU(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-    int rc = enqueue_pyramids(h, d_a, d_b, pitch);
+    int rc = enqueue_pyramids(h);
     if (rc == DIS_OK) rc = enqueue_engine(h, nullptr);
-    if (rc == DIS_OK) rc = enqueue_finish(h, d_out);
+    if (rc == DIS_OK) rc = enqueue_finish(h);
     cudaGraph_t g = nullptr;
     cudaError_t e = cudaStreamEndCapture(h->stream, &g);
     if (rc != DIS_OK) {
@@ -404,25 +458,22 @@ int enqueue_run_device(dis_handle* h, const uint8_t* d_a, const uint8_t* d_b, in
     e = cudaGraphInstantiate(&h->graph_exec, g, 0);
     cudaGraphDestroy(g);
     if (e != cudaSuccess) return fail(h, DIS_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
-    h->graph_a = d_a;
-    h->graph_b = d_b;
-    h->graph_out = d_out;
     h->graph_w = h->w_org;
     h->graph_h = h->h_org;
     h->tm.launches = h->launches;
     CU(h, cudaGraphLaunch(h->graph_exec, h->stream));
     return DIS_OK;
   }
-  h->launches = 0;
+  h->launches = 1;
   int rc;
   {
     StageClock ck(h, &h->tm.pyramid_ms);
-    rc = enqueue_pyramids(h, d_a, d_b, pitch);
+    rc = enqueue_pyramids(h);
   }
   if (rc == DIS_OK) rc = enqueue_engine(h, nullptr);
   if (rc == DIS_OK) {
     StageClock ck(h, &h->tm.finish_ms);
-    rc = enqueue_finish(h, d_out);
+    rc = enqueue_finish(h);
   }
   h->tm.launches = h->launches;
   return rc;
@@ -641,6 +692,22 @@ int dis_fetch_tap(dis_handle* h, int tap, int level, float* out, size_t n_floats
     if (n_floats < v.size()) return fail(h, DIS_ERR_INVALID_ARG, "tap buffer too small");
     memcpy(out, v.data(), v.size() * sizeof(float));
   }
+  return DIS_OK;
+}
+
+int dis_enable_kernel_profile(dis_handle* h, int on) {
+  if (!h) return DIS_ERR_INVALID_ARG;
+  h->kprof_on = on != 0;
+  h->kprof.st = h->stream;
+  h->kprof.recs.clear();
+  return DIS_OK;
+}
+
+int dis_get_kernel_profile(dis_handle* h, dis_kernel_time* out, int cap, int* n) {
+  if (!h || !n) return DIS_ERR_INVALID_ARG;
+  *n = (int)h->kprof.recs.size();
+  if (out)
+    for (int i = 0; i < *n && i < cap; ++i) out[i] = h->kprof.recs[i];
   return DIS_OK;
 }
 

@@ -10,7 +10,8 @@ namespace {
 
 __global__ void __launch_bounds__(256) k_finish(const float2* __restrict__ fl, int wl, int hl, int lv_l,
                                                 int left, int top, int w_org, int h_org,
-                                                float2* __restrict__ out) {
+                                                const Mailbox* __restrict__ mb) {
+  float2* __restrict__ out = mb->out;
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= w_org || y >= h_org) return;
@@ -44,9 +45,9 @@ __global__ void __launch_bounds__(256) k_finish(const float2* __restrict__ fl, i
 }  // namespace
 
 void launch_finish(const float2* flow_l, int wl, int hl, int lv_l, int left, int top, int w_org, int h_org,
-                   float2* out, cudaStream_t st) {
+                   const Mailbox* mb, cudaStream_t st) {
   dim3 block(32, 8), grid((w_org + 31) / 32, (h_org + 7) / 8);
-  k_finish<<<grid, block, 0, st>>>(flow_l, wl, hl, lv_l, left, top, w_org, h_org, out);
+  k_finish<<<grid, block, 0, st>>>(flow_l, wl, hl, lv_l, left, top, w_org, h_org, mb);
 }
 
 }  // namespace dis

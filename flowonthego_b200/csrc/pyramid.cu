@@ -17,8 +17,14 @@ namespace dis {
 namespace {
 
 struct SrcU8 {
+  const Mailbox* mb;
+  int which;
   const uint8_t* p;
   int w_org, h_org, pitch, left, top;
+  __device__ __forceinline__ void resolve() {
+    p = which ? mb->b : mb->a;
+    pitch = mb->pitch;
+  }
   __device__ __forceinline__ float at(int x, int y) const {
     int sx = min(max(x - left, 0), w_org - 1);
     int sy = min(max(y - top, 0), h_org - 1);
@@ -29,6 +35,7 @@ struct SrcU8 {
 struct SrcDown {  // 2x2 mean of the finer level (padded array, pad offset applied)
   const float* p;
   int pitch, pad;
+  __device__ __forceinline__ void resolve() {}
   __device__ __forceinline__ float at(int x, int y) const {
     const float* r0 = p + (size_t)(2 * y + pad) * pitch + 2 * x + pad;
     const float2 a = make_float2(__ldg(r0), __ldg(r0 + 1));
@@ -45,7 +52,8 @@ __global__ void __launch_bounds__(256) k_pyr_level(Src sa, Src sb, int w, int h,
   const int Y = blockIdx.y * blockDim.y + threadIdx.y;
   if (X0 >= pitch || Y >= th) return;
   const bool second = blockIdx.z == 1;
-  const Src s = second ? sb : sa;
+  Src s = second ? sb : sa;
+  s.resolve();
   float* I = second ? Ib : Ia;
   float* Gx = second ? Ibx : Iax;
   float* Gy = second ? Iby : Iay;
@@ -88,11 +96,21 @@ void launch(Src sa, Src sb, const LevelGeom& g, float* Ia, float* Iax, float* Ia
 
 }  // namespace
 
-void launch_level0(const uint8_t* src_a, const uint8_t* src_b, int w_org, int h_org, int src_pitch,
-                   int left, int top, const LevelGeom& g, float* Ia, float* Iax, float* Iay, float* Ib,
-                   float* Ibx, float* Iby, cudaStream_t st) {
-  SrcU8 sa{src_a, w_org, h_org, src_pitch, left, top};
-  SrcU8 sb{src_b, w_org, h_org, src_pitch, left, top};
+__global__ void k_set_mailbox(Mailbox* mb, const uint8_t* a, const uint8_t* b, float2* out, int pitch) {
+  mb->a = a;
+  mb->b = b;
+  mb->out = out;
+  mb->pitch = pitch;
+}
+
+void launch_set_mailbox(Mailbox* mb, const uint8_t* a, const uint8_t* b, float2* out, int pitch, cudaStream_t st) {
+  k_set_mailbox<<<1, 1, 0, st>>>(mb, a, b, out, pitch);
+}
+
+void launch_level0(const Mailbox* mb, int w_org, int h_org, int left, int top, const LevelGeom& g, float* Ia,
+                   float* Iax, float* Iay, float* Ib, float* Ibx, float* Iby, cudaStream_t st) {
+  SrcU8 sa{mb, 0, nullptr, w_org, h_org, 0, left, top};
+  SrcU8 sb{mb, 1, nullptr, w_org, h_org, 0, left, top};
   launch(sa, sb, g, Ia, Iax, Iay, Ib, Ibx, Iby, st);
 }
 

@@ -402,28 +402,49 @@ size_t varref_progress_ints(int h, int n_solver) { return (size_t)n_solver * ((h
 
 // Returns the number of kernels launched, or -1 for an unsupported level shape.
 int launch_varref(const LevelGeom& g, const VarParams& v, const float* I0, const float* I1, float2* flow,
-                  const VarRefBuffers& b, cudaStream_t st) {
+                  const VarRefBuffers& b, cudaStream_t st, Prof* prof) {
   const int w = g.w, h = g.h, n = w * h;
   if (w < 2 || h < 4 || v.n_solver < 1) return -1;  // reference would take its slow path / read out of range
   int launches = 0;
   dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
-  k_warp<<<grid, block, 0, st>>>(w, h, g.pad, g.pitch, I0, I1, flow, b.avg, b.Iz, b.mask);
-  k_deriv1<<<grid, block, 0, st>>>(w, h, b.avg, b.Iz, b.Ix, b.Iy, b.Ixz, b.Iyz);
-  k_deriv2<<<grid, block, 0, st>>>(w, h, b.Ix, b.Iy, b.Ixx, b.Ixy, b.Iyy);
+  // algorithmic bytes per SURVEY.md section 8(d): warp+mask 28 B/px, derivative stack 40 B/px
+  {
+    ProfScope ps(prof, "k_warp", g.lv, 28.0 * n);
+    k_warp<<<grid, block, 0, st>>>(w, h, g.pad, g.pitch, I0, I1, flow, b.avg, b.Iz, b.mask);
+  }
+  {
+    ProfScope ps(prof, "k_deriv1", g.lv, 24.0 * n);
+    k_deriv1<<<grid, block, 0, st>>>(w, h, b.avg, b.Iz, b.Ix, b.Iy, b.Ixz, b.Iyz);
+  }
+  {
+    ProfScope ps(prof, "k_deriv2", g.lv, 16.0 * n);
+    k_deriv2<<<grid, block, 0, st>>>(w, h, b.Ix, b.Iy, b.Ixx, b.Ixy, b.Iyy);
+  }
   launches += 3;
   if (v.n_inner <= 0) return launches;
   const int K = (h + 31) / 32, T = v.n_solver;
   for (int it = 0; it < v.n_inner; ++it) {
     AssembleArgs aa{w, h, v.qa, v.hg, v.hd, it == 0 ? 1 : 0, flow, b.duv, b.mask, b.Ix, b.Iy, b.Iz,
                     b.Ixx, b.Ixy, b.Iyy, b.Ixz, b.Iyz, b.a11, b.a12, b.a22, b.b, b.hv};
-    k_assemble<<<grid, block, 0, st>>>(aa);
+    {
+      // smoothness 16 + data term 64 + sub_laplacian 32 + flow update 24 B/px
+      ProfScope ps(prof, "k_assemble", g.lv, 136.0 * n);
+      k_assemble<<<grid, block, 0, st>>>(aa);
+    }
     if (it == 0) cudaMemsetAsync(b.duv, 0, sizeof(float2) * n, st);
     cudaMemsetAsync(b.progress, 0, sizeof(int) * (T * K + 1), st);
     SorArgs sa{w, h, T, K, v.omega, b.a11, b.a12, b.a22, b.b, b.hv, b.duv, b.progress};
-    k_sor_wavefront<<<T * K, 32, 0, st>>>(sa);
+    {
+      // each sweep reads 9 arrays and writes 2: 44 B/px
+      ProfScope ps(prof, "k_sor_wavefront", g.lv, 44.0 * T * n);
+      k_sor_wavefront<<<T * K, 32, 0, st>>>(sa);
+    }
     launches += 2;
   }
-  k_update<<<(n + 255) / 256, 256, 0, st>>>(n, flow, b.duv);
+  {
+    ProfScope ps(prof, "k_update", g.lv, 8.0 * n);
+    k_update<<<(n + 255) / 256, 256, 0, st>>>(n, flow, b.duv);
+  }
   return launches + 1;
 }
 

@@ -171,6 +171,19 @@ typedef enum dis_tap {
 int dis_enable_taps(dis_handle* h, int on);
 int dis_fetch_tap(dis_handle* h, int tap, int level, float* out, size_t n_floats, size_t* n_written);
 
+/* ---- per-kernel device timing (bench.py's roofline leg; never on the timed path) ---------- */
+typedef struct dis_kernel_time {
+  char name[32];     /* kernel name, e.g. "k_sor_wavefront"                                  */
+  int32_t level;     /* pyramid level                                                        */
+  int32_t launches;  /* launches accumulated                                                 */
+  float ms;          /* sum of CUDA-event durations over those launches                      */
+  double alg_bytes;  /* sum of ALGORITHMIC bytes (SURVEY.md section 8(d) model) over them     */
+} dis_kernel_time;
+/* While on, runs are not replayed from the CUDA graph and every launch is bracketed by events. */
+int dis_enable_kernel_profile(dis_handle* h, int on);
+/* Copies up to `cap` accumulated records (one per kernel and level); *n receives the count. */
+int dis_get_kernel_profile(dis_handle* h, dis_kernel_time* out, int cap, int* n);
+
 /* Library identification: "dis_b200 <version> sm_100a". */
 const char* dis_version(void);
 

@@ -1,0 +1,101 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol include/dis_c.h
+declares, parameter handling mirrors kroeger/run_dense.cpp, .flo I/O round-trips, and the product
+fails loudly without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import flowonthego_b200 as F
+from flowonthego_b200 import api
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "dis_c.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(dis_[a-z0-9_]+)\s*\(", hdr))
+    assert {"dis_create", "dis_run_pyramids", "dis_run_u8", "dis_submit_u8_device", "dis_write_flo"} <= names
+    L = F.lib()
+    for n in sorted(names):
+        assert hasattr(L, n), "libdis_b200.so does not export " + n
+    assert b"sm_100a" in L.dis_version()
+
+
+def test_presets_follow_reference_cli():
+    # kroeger/run_dense.cpp:239-267 on a 1024-wide image
+    expect = {1: (8, 0.3, 5, 3, 16, 0), 2: (8, 0.4, 5, 3, 12, 1), 3: (12, 0.75, 5, 1, 16, 1), 4: (12, 0.75, 5, 0, 128, 1)}
+    for k, (ps, ov, lf, ll, it, tv) in expect.items():
+        p = F.Params.preset(k, 1024)
+        assert (p.patchsz, p.lv_f, p.lv_l, p.maxiter, p.miniter, p.usetvref) == (ps, lf, ll, it, it, tv)
+        assert abs(p.poverl - ov) < 1e-7
+    assert F.Params.preset(7, 1024).to_dict() == F.Params.preset(2, 1024).to_dict()  # `default:` label
+    assert F.lib().dis_auto_first_scale(1920, 5, 12) == 6 and F.lib().dis_auto_first_scale(3840, 5, 12) == 7
+    assert F.lib().dis_auto_first_scale(10, 5, 12) == 0
+
+
+def test_params_from_argv_order():
+    argv = "5 3 12 12 0.05 0.95 0 8 0.40 0 1 0 1 10 10 5 1 3 1.6 2".split()  # kroeger/README.md:62
+    p = F.Params.from_argv(argv)
+    d = p.to_dict()
+    assert [d[k] for k in ("lv_f", "lv_l", "maxiter", "miniter", "patchsz", "usefbcon", "patnorm", "costfct",
+                           "usetvref", "tv_innerit", "tv_solverit", "verbosity")] == [5, 3, 12, 12, 8, 0, 1, 0, 1, 1, 3, 2]
+    assert np.float32(d["tv_sor"]) == np.float32(1.6) and np.float32(d["poverl"]) == np.float32(0.4)
+    with pytest.raises(F.DisError):
+        F.Params.from_argv(argv[:19])
+
+
+def test_validate_rejects_out_of_scope():
+    L = F.lib()
+    buf = ctypes.create_string_buffer(200)
+    ok = F.Params.preset(2, 1024)
+    assert L.dis_params_validate(ctypes.byref(ok), buf, 200) == 0
+    for kw in (dict(patchsz=7), dict(patchsz=18), dict(lv_l=6), dict(costfct=10), dict(poverl=1.0), dict(tv_solverit=0)):
+        bad = ok.copy(**kw)
+        assert L.dis_params_validate(ctypes.byref(bad), buf, 200) != 0, kw
+        assert len(buf.value) > 0
+
+
+def test_padded_size_matches_reference():
+    # kroeger/run_dense.cpp:298-311: 1024x436 at lv_f=5 -> 1024x448, pad split floor/ceil
+    assert F.padded_size(1024, 436, 5) == (1024, 448, 0, 6)
+    assert F.padded_size(1920, 1080, 6) == (1920, 1088, 0, 4)
+    assert F.padded_size(3840, 2160, 7) == (3840, 2176, 0, 8)
+    assert F.padded_size(501, 301, 3) == (504, 304, 1, 1)
+
+
+def test_flo_round_trip(tmp_path):
+    rng = np.random.default_rng(0)
+    fl = rng.standard_normal((7, 13, 2)).astype(np.float32)
+    path = str(tmp_path / "x.flo")
+    F.write_flo(path, fl)
+    raw = open(path, "rb").read()
+    assert raw[:4] == b"PIEH" and len(raw) == 12 + 8 * 7 * 13  # flow_code/C/flowIO.cpp:5-25
+    assert np.frombuffer(raw[4:12], np.int32).tolist() == [13, 7]
+    assert np.array_equal(F.read_flo(path), fl)
+    open(path, "wb").write(b"XXXX" + raw[4:])
+    with pytest.raises(F.DisError):
+        F.read_flo(path)
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the engine must refuse to exist (and say why)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(F.DisError) as ei:
+        F.Engine(F.Params.preset(2, 256), 256, 192)
+    assert ei.value.code == 3 and "no CPU path" in str(ei.value)
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under flowonthego_b200/ or bench.py's product arm may use it."""
+    pkg = os.path.join(ROOT, "flowonthego_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src.replace("# oracle-free", ""), os.path.join(dp, f)
