@@ -87,13 +87,13 @@ void launch_densify(const DensifyArgs& a, cudaStream_t st);
 // varref.cu
 struct VarRefBuffers {
   float *avg, *Iz, *mask, *Ix, *Iy, *Ixx, *Ixy, *Iyy, *Ixz, *Iyz;  // planar, w*h
-  float *a11, *a12, *a22;                                          // inverted 2x2 blocks
-  float2 *b, *hv, *duv;                                            // (b1,b2), (horiz,vert), (du,dv)
-  int* progress;                                                   // SOR wavefront flags
+  float4 *coefA, *coefB;  // wavefront-major {a11,a12,a22,horiz} (inverted 2x2 blocks) and {b1,b2,vert,-}
+  float4* du4;            // wavefront-major records {du, dv, tag, -}
+  int* progress;          // SOR wavefront flags: counters, ticket, epoch
 };
 int launch_varref(const LevelGeom& g, const VarParams& v, const float* I0, const float* I1,
                   float2* flow, const VarRefBuffers& b, cudaStream_t st, Prof* prof = nullptr);
-size_t varref_progress_ints(int h, int n_solver);
+void varref_sizes(int w, int h, int n_solver, size_t* n_coef4, size_t* n_du4, size_t* n_prog);
 // finish.cu
 void launch_finish(const float2* flow_l, int wl, int hl, int lv_l, int left, int top, int w_org,
                    int h_org, const Mailbox* mb, cudaStream_t st);

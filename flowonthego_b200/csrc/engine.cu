@@ -225,13 +225,14 @@ size_t carve(dis_handle* h, int w, int h_img, char* base, bool assign) {
   VarRefBuffers vb{};
   if (q.usetvref) {
     const size_t n = (size_t)gf.w * gf.h;
-    float** planes[] = {&vb.avg, &vb.Iz, &vb.mask, &vb.Ix, &vb.Iy, &vb.Ixx, &vb.Ixy,
-                        &vb.Iyy, &vb.Ixz, &vb.Iyz, &vb.a11, &vb.a12, &vb.a22};
+    float** planes[] = {&vb.avg, &vb.Iz, &vb.mask, &vb.Ix, &vb.Iy, &vb.Ixx, &vb.Ixy, &vb.Iyy, &vb.Ixz, &vb.Iyz};
     for (float** p : planes) *p = c.take<float>(n);
-    vb.b = c.take<float2>(n);
-    vb.hv = c.take<float2>(n);
-    vb.duv = c.take<float2>(n);
-    vb.progress = c.take<int>(varref_progress_ints(gf.h, std::max(1, q.tv_solverit)));
+    size_t n_coef4, n_du4, n_prog;
+    varref_sizes(gf.w, gf.h, std::max(1, q.tv_solverit), &n_coef4, &n_du4, &n_prog);
+    vb.coefA = c.take<float4>(n_coef4);
+    vb.coefB = c.take<float4>(n_coef4);
+    vb.du4 = c.take<float4>(n_du4);
+    vb.progress = c.take<int>(n_prog);
   }
   float2* d_out = c.take<float2>((size_t)w * h_img);
   Mailbox* mailbox = c.take<Mailbox>(1);
@@ -280,6 +281,8 @@ int plan(dis_handle* h, int w, int h_img) {
   }
   drop_graph(h);
   carve(h, w, h_img, h->slab, true);
+  // SOR hand-off tags/epoch start from a clean slate (stale bytes could alias a tag)
+  CU(h, cudaMemsetAsync(h->slab, 0, h->slab_bytes, h->stream));
   // coarsest level must be large enough for the kernels (and for the reference itself)
   const LevelGeom& gc = h->lv[h->P.lv_f].g;
   if (gc.w < 2 || gc.h < 4)

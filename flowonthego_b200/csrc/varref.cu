@@ -18,11 +18,22 @@
 //
 // SOR keeps the reference's *lexicographic* Gauss-Seidel dependency order exactly (pixel (i,j)
 // sees new (i-1,j), new (i,j-1), old (i+1,j), old (i,j+1)) by sweeping a skewed wavefront: one
-// warp owns 32 consecutive rows, lane l works on column s-l at step s, so the upper neighbour
-// is the previous step's result of lane l-1 (one shuffle) and the left neighbour is the lane's
-// own previous result.  Row blocks and successive sweeps chase each other through per-item
-// progress counters in global memory (items are handed out through a ticket in dependency
-// order, so a running warp only ever waits for warps that have already started).
+// warp owns 32 consecutive rows ("row block"), lane l works on column s - SK*l at step s, so the
+// upper neighbour is lane l-1's result of SK steps ago (one shuffle, off the critical path for
+// SK = 2) and the left neighbour is the lane's own previous result.
+//
+// Wavefront-major layout: everything the sweep touches is stored per row block as [step][lane]
+// (element (row 32k+l, column i) lives at step s = i + SK*l), so each step of a warp is one
+// fully coalesced 512-byte access per array -- {a11,a12,a22,horiz} and {b1,b2,vert,-} as two
+// float4 streams, (du,dv) as float4 pairs of two consecutive steps -- prefetched D steps ahead
+// into a small shared-memory ring with cp.async.cg (L1 is bypassed: other SMs write these lines).
+// Row blocks hand their last row to the block below through a flag-in-data boundary buffer
+// (16-byte {du,dv,tag} stores, no fences); successive sweeps chase each other through coarse
+// progress counters.  Items (sweep t, row block k) are handed out through a ticket in
+// dependency order, so a running warp only ever waits for warps that have already started.
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace dis {
@@ -122,22 +133,36 @@ __global__ void __launch_bounds__(256) k_deriv2(int w, int h, const float* __res
 }
 
 // ---- one inner fixed-point iteration: smoothness + data term + Laplacian RHS + block inverse ----
+constexpr int SK = 2;  // wavefront skew (columns per row)
+
+// wavefront-major addressing of one level
+struct Skew {
+  int w, h, K, nsteps, nsp;  // nsp: steps per row block as allocated (whole TMA chunks + prefetch overrun)
+  __host__ __device__ Skew(int w_, int h_)
+      : w(w_), h(h_), K((h_ + 31) / 32), nsteps(w_ + SK * 31), nsp((w_ + SK * 31 + 15) / 16 * 16 + 32) {}
+  __host__ __device__ size_t at(int i, int j) const {  // float4 index of pixel (i,j)
+    const int k = j >> 5, l = j & 31;
+    return ((size_t)k * nsp + i + SK * l) * 32 + l;
+  }
+};
+
 struct AssembleArgs {
   int w, h;
   float qa, hg, hd;
   int first;  // first inner iteration: uu = wx (memcpy), du = dv = 0
   const float2* flow;  // wx, wy
-  const float2* duv;
+  const float4* du4;   // (du,dv) records, wavefront-major
   const float *mask, *Ix, *Iy, *Iz, *Ixx, *Ixy, *Iyy, *Ixz, *Iyz;
-  float *a11, *a12, *a22;
-  float2 *b, *hv;
+  float4 *coefA, *coefB;  // {a11,a12,a22,horiz}, {b1,b2,vert,0}, wavefront-major
+  int* prog;              // SOR flags: [0] epoch, [1] ticket, [2..2+n_prog) per-item progress counters
+  int n_prog;
 };
 
 __device__ __forceinline__ float2 uu_at(const AssembleArgs& a, int i, int j) {
   const int o = j * a.w + i;
   const float2 f = a.flow[o];
   if (a.first) return f;
-  const float2 d = a.duv[o];
+  const float4 d = a.du4[Skew(a.w, a.h).at(i, j)];
   return make_float2(f.x + d.x, f.y + d.y);  // refine_variational.cpp:212-213
 }
 
@@ -170,6 +195,11 @@ __global__ void __launch_bounds__(256) k_assemble(const AssembleArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   const int w = a.w, h = a.h;
+  if (blockIdx.x == 0 && blockIdx.y == 0) {  // reset the SOR flags of the sweep that follows
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    for (int q = tid; q <= a.n_prog; q += blockDim.x * blockDim.y) a.prog[1 + q] = 0;  // ticket + counters
+    if (tid == 0) a.prog[0] += 1;  // epoch: makes the boundary tags of every launch unique
+  }
   if (i >= w || j >= h) return;
   const int o = j * w + i;
   // compute_smoothness: horiz(i,j) = s(i,j)+s(i+1,j) (0 for i >= w-1), vert likewise
@@ -180,7 +210,12 @@ __global__ void __launch_bounds__(256) k_assemble(const AssembleArgs a) {
   const float vt = (j > 0) ? smooth_at(a, i, j - 1) + sc : 0.0f;
 
   // compute_data, 1-channel branch
-  const float2 d = a.first ? make_float2(0.0f, 0.0f) : a.duv[o];
+  const Skew sk(w, h);
+  float2 d = make_float2(0.0f, 0.0f);
+  if (!a.first) {
+    const float4 q = a.du4[sk.at(i, j)];
+    d = make_float2(q.x, q.y);
+  }
   const float du = d.x, dv = d.y;
   const float mk = a.mask[o];
   const float ix = a.Ix[o], iy = a.Iy[o], iz = a.Iz[o];
@@ -249,32 +284,84 @@ __global__ void __launch_bounds__(256) k_assemble(const AssembleArgs a) {
     dpsis = hl + hr + vt + vb;
   const float iA11 = A22 + dpsis, iA22 = A11 + dpsis;
   const float det = iA11 * iA22 - A12 * A12;
-  a.a11[o] = iA11 / det;
-  a.a22[o] = iA22 / det;
-  a.a12[o] = A12 / (-det);
-  a.b[o] = make_float2(B1, B2);
-  a.hv[o] = make_float2(hr, vb);
+  const size_t oc = sk.at(i, j);
+  a.coefA[oc] = make_float4(iA11 / det, A12 / (-det), iA22 / det, hr);
+  a.coefB[oc] = make_float4(B1, B2, vb, 0.0f);
 }
 
 // ---- sor_coupled: exact lexicographic sweeps as a skewed wavefront ------------------------------
 struct SorArgs {
   int w, h, T, K;  // T sweeps, K = ceil(h/32) row blocks
   float omega;
-  const float *a11, *a12, *a22;
-  const float2 *b, *hv;
-  float2* duv;
-  int* prog;  // [T*K] completed steps per item, then [1] ticket
+  const float4 *coefA, *coefB;  // wavefront-major [K][nsp][32]
+  float4* du4;                  // wavefront-major records {du, dv, tag, -}: [K+1][nsp][32]
+  int* prog;                    // [0] epoch, [1] ticket, [2 + t*K + k] pacing hint: completed steps of item (t,k)
 };
 
-constexpr int kSorPublish = 8;  // publish progress every this many steps
+constexpr int kCH = 16;       // steps per TMA chunk of the coefficient streams
+constexpr int kNS = 4;        // TMA stages in flight
+constexpr int kL = 16;        // prefetch lead (steps) of the (du,dv) record streams
+constexpr int kRD = 64;       // record ring slots (power of two > kL + 3)
+constexpr int kPublish = 8;   // pacing hint granularity (steps)
+constexpr size_t kSorSmem = (size_t)kNS * kCH * 32 * 16 * 2 + (size_t)kRD * 32 * 16 + 3 * kRD * 16 + kNS * 8;
 
 __device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ float4 ld_volatile4(const float4* p) {
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+// TMA (bulk async copy) + mbarrier
+__device__ __forceinline__ void mbar_init(void* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, void* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
 
 __global__ void __launch_bounds__(32) k_sor_wavefront(const SorArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* const sA = smem_raw;                                          // [kNS*kCH][32] float4
+  unsigned char* const sB = smem_raw + (size_t)kNS * kCH * 512;                // [kNS*kCH][32] float4
+  unsigned char* const sD = smem_raw + (size_t)kNS * kCH * 1024;               // [kRD][32] float4, slot x: old[x+2]
+  unsigned char* const sUp = sD + (size_t)kRD * 512;                           // [kRD] float4
+  unsigned char* const sDn = sUp + kRD * 16;                                   // [kRD] float4
+  unsigned char* const sVt = sDn + kRD * 16;                                   // [kRD] float4
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(sVt + kRD * 16);  // [kNS]
+
   const int lane = threadIdx.x;
   const int w = a.w, h = a.h, T = a.T, K = a.K;
+  const Skew sk(w, h);
+  const int nsteps = sk.nsteps, nsp = sk.nsp;
   int tk = 0;
-  if (lane == 0) tk = atomicAdd(a.prog + T * K, 1);
+  if (lane == 0) tk = atomicAdd(a.prog + 1, 1);
   tk = __shfl_sync(FULL, tk, 0);
   // decode ticket -> (t,k): items ordered by key = 2t + k, so that (t,k-1), (t-1,k), (t-1,k+1)
   // all hold smaller tickets
@@ -295,116 +382,223 @@ __global__ void __launch_bounds__(32) k_sor_wavefront(const SorArgs a) {
   }
   if (t < 0) return;
   const int j = k * 32 + lane;
-  const bool rowok = j < h;
-  const int total = w + 31;
-  const int* p_up = (k > 0) ? a.prog + t * K + k - 1 : nullptr;
-  const int* p_prev = (t > 0) ? a.prog + (t - 1) * K + k : nullptr;
-  const int* p_below = (t > 0 && k < K - 1) ? a.prog + (t - 1) * K + k + 1 : nullptr;
-  int seen_up = 0, seen_prev = 0, seen_below = 0;
-  float2 res_prev = make_float2(0.0f, 0.0f);    // my result of the previous step (new (i-1,j))
-  float2 right_prev = make_float2(0.0f, 0.0f);  // old (i,j), loaded as "right" one step earlier
-  float hl = 0.0f;                              // horiz(i-1,j); 0 in the first column (f1[0] = 0)
-  float v_prev = 0.0f;                          // vert(i-1..): my vert weight of the previous step
+  const bool has_up = k > 0, has_dn = (k < K - 1);
+  const bool no_up = (j == 0), no_dn = (j >= h - 1);
+  const int epoch = ld_volatile(a.prog);
+  const int tag_cur = (epoch << 5) | t, tag_prev = (epoch << 5) | (t - 1);  // epoch >= 1, T <= 32
+  const bool chk_old = (t > 0);                           // my old records carry the previous sweep's tag
+  const int* p_prev = (t > 0) ? a.prog + 2 + (t - 1) * K + k : nullptr;                // same block, previous sweep
+  const int* p_upb = has_up ? a.prog + 2 + t * K + k - 1 : nullptr;                     // block above, same sweep
+  const int* p_dnb = (t > 0 && has_dn) ? a.prog + 2 + (t - 1) * K + k + 1 : nullptr;    // block below, previous sweep
+  int seen_prev = 0, seen_upb = 0, seen_dnb = 0;
+  const float4* gA = a.coefA + (size_t)k * nsp * 32;
+  const float4* gB = a.coefB + (size_t)k * nsp * 32;
+  float4* gD = a.du4 + (size_t)k * nsp * 32 + lane;                             // my records
+  const float4* gUp = a.du4 + ((size_t)(has_up ? k - 1 : 0) * nsp) * 32 + 31;  // block above, lane 31
+  const float4* gDn = a.du4 + ((size_t)(k + 1) * nsp) * 32;                    // block below, lane 0
+  const float4* gVt = a.coefB + ((size_t)(has_up ? k - 1 : 0) * nsp) * 32 + 31;
   const float omega = a.omega;
+  const int nchunks = (nsteps + kCH - 1) / kCH;
 
-  for (int s = 0; s < total; ++s) {
-    // ---- wait for the producers of this step
-    {
-      bool polled = false;
-      if (p_up) {
-        const int need = min(s + 32, total);
-        if (seen_up < need) {
-          do seen_up = ld_volatile(p_up); while (seen_up < need);
-          polled = true;
-        }
-      }
-      if (p_prev) {
-        const int need = min(s + 2, total);
-        if (seen_prev < need) {
-          do seen_prev = ld_volatile(p_prev); while (seen_prev < need);
-          polled = true;
-        }
-      }
-      if (p_below) {
-        const int need = min(max(s - 30, 0), total);
-        if (seen_below < need) {
-          do seen_below = ld_volatile(p_below); while (seen_below < need);
-          polled = true;
-        }
-      }
-      if (polled) __threadfence();
-    }
-    const int i = s - lane;
-    const bool act = rowok && i >= 0 && i < w;
-    float2 up = make_float2(__shfl_up_sync(FULL, res_prev.x, 1), __shfl_up_sync(FULL, res_prev.y, 1));
-    float vt = __shfl_up_sync(FULL, v_prev, 1);
-    if (act) {
-      const int o = j * w + i;
-      if (lane == 0 && j > 0) {
-        up = __ldcg(a.duv + o - w);
-        vt = __ldg(a.hv + o - w).y;
-      }
-      const float2 hvv = __ldg(a.hv + o);
-      const float2 bb = __ldg(a.b + o);
-      const float A11 = __ldg(a.a11 + o), A12 = __ldg(a.a12 + o), A22 = __ldg(a.a22 + o);
-      const float2 right = (i < w - 1) ? __ldcg(a.duv + o + 1) : make_float2(0.0f, 0.0f);
-      const float2 self = (i == 0) ? __ldcg(a.duv + o) : right_prev;
-      float s1, s2;
-      if (j == 0) {
-        const float2 below = __ldcg(a.duv + o + w);
-        s1 = hvv.x * right.x + hvv.y * below.x + bb.x;
-        s2 = hvv.x * right.y + hvv.y * below.y + bb.y;
-      } else if (j == h - 1) {
-        s1 = hvv.x * right.x + vt * up.x + bb.x;
-        s2 = hvv.x * right.y + vt * up.y + bb.y;
-      } else {
-        const float2 below = __ldcg(a.duv + o + w);
-        s1 = hvv.x * right.x + vt * up.x + hvv.y * below.x + bb.x;
-        s2 = hvv.x * right.y + vt * up.y + hvv.y * below.y + bb.y;
-      }
-      float B1, B2;
-      if (i == 0) {
-        B1 = s1;
-        B2 = s2;
-      } else {
-        B1 = hl * res_prev.x + s1;
-        B2 = hl * res_prev.y + s2;
-      }
-      float2 nv;
-      nv.x = self.x + omega * (A11 * B1 + A12 * B2 - self.x);
-      nv.y = self.y + omega * (A12 * B1 + A22 * B2 - self.y);
-      __stcg(a.duv + o, nv);
-      res_prev = nv;
-      right_prev = right;
-      hl = hvv.x;
-      v_prev = hvv.y;
-    }
-    // ---- publish progress
-    if (((s + 1) % kSorPublish) == 0 || s + 1 == total) {
-      __threadfence();
-      __syncwarp();
-      if (lane == 0) *reinterpret_cast<volatile int*>(a.prog + t * K + k) = s + 1;
-    }
+  // ---- coefficient streams: TMA bulk copies of kCH steps (8 KB per array) into a kNS-stage ring
+  if (lane == 0) {
+    for (int q = 0; q < kNS; ++q) mbar_init(&bars[q], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   }
+  __syncwarp();
+  auto tma_chunk = [&](int c) {  // lane 0 only
+    const int st = c % kNS;
+    mbar_expect_tx(&bars[st], 2 * kCH * 512);
+    tma_bulk_g2s(sA + (size_t)st * kCH * 512, gA + (size_t)c * kCH * 32, kCH * 512, &bars[st]);
+    tma_bulk_g2s(sB + (size_t)st * kCH * 512, gB + (size_t)c * kCH * 32, kCH * 512, &bars[st]);
+  };
+  if (lane == 0)
+    for (int c = 0; c < kNS && c < nchunks; ++c) tma_chunk(c);
+
+  // ---- record streams in groups of 8 steps: paced by the producers' progress hints, validated by tag
+  auto pace = [&](const int* p, int& seen, int need) {
+    need = min(need, nsteps);
+    if (p && seen < need) {
+      do seen = ld_volatile(p); while (seen < need);
+    }
+  };
+  const unsigned sD_u = smem_u32(sD) + lane * 16, sUp_u = smem_u32(sUp), sDn_u = smem_u32(sDn), sVt_u = smem_u32(sVt);
+  // loads that steps x0..x0+7 will consume.  Addresses past a row block's end fall into the next block's
+  // (allocated) storage and are never used, so nothing here is predicated on the column range.
+  auto tick8 = [&](int x0) {
+    pace(p_prev, seen_prev, x0 + 7 + 2 + 1);
+    pace(p_upb, seen_upb, min(x0 + 7, w - 1) + 31 * SK + 1);
+    pace(p_dnb, seen_dnb, min(x0 + 7 - 31 * SK, w - 1) + 1);
+    const unsigned slot = (unsigned)(x0 & (kRD - 1));
+    const float4* src = gD + (size_t)(x0 + 2) * 32;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sD_u + ((slot + q) << 9)), "l"(src + q * 32) : "memory");
+    if (lane < 8 && has_up) {  // lane q: column x0+q of the row above = block k-1, lane 31, step x0+q + 31*SK
+      const size_t o = (size_t)(x0 + lane + 31 * SK) * 32;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sUp_u + ((slot + lane) << 4)), "l"(gUp + o) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sVt_u + ((slot + lane) << 4)), "l"(gVt + o) : "memory");
+    }
+    if (lane >= 24 && has_dn) {  // lane 24+q: column x0+q - 31*SK of the row below = block k+1, lane 0
+      const long long o = (long long)(x0 + (lane - 24) - 31 * SK) * 32;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sDn_u + ((slot + lane - 24) << 4)), "l"(gDn + o) : "memory");
+    }
+    cp_async_commit();
+  };
+  pace(p_prev, seen_prev, 2);
+  float4 rec0 = ld_volatile4(gD), rec1 = ld_volatile4(gD + 32);
+  if (chk_old) {
+    while (__float_as_int(rec0.z) != tag_prev) rec0 = ld_volatile4(gD);
+    while (__float_as_int(rec1.z) != tag_prev) rec1 = ld_volatile4(gD + 32);
+  }
+  tick8(0);
+  tick8(8);
+
+  float2 self_old = make_float2(rec0.x, rec0.y);  // old[s]   (lane 0's first "self" is old[0])
+  float2 old1 = make_float2(rec1.x, rec1.y);      // old[s+1]
+  float2 res1 = make_float2(0.f, 0.f), res2 = make_float2(0.f, 0.f);  // my results 1 and 2 steps ago
+  float v1 = 0.f, v2 = 0.f;                                           // my vert weights 1 and 2 steps ago
+  float hl = 0.f;                                                     // horiz(i-1,j)
+  int i = -SK * lane;                                                 // my column at step s
+  float4* gOut = gD;
+  volatile int* my_hint = a.prog + 2 + t * K + k;
+  const float tagf = __int_as_float(tag_cur);
+
+  for (int c = 0; c < nchunks; ++c) {
+    const int st = c % kNS;
+    mbar_wait(&bars[st], (unsigned)(c / kNS) & 1u);
+    const unsigned char* cA_p = sA + (size_t)st * kCH * 512 + lane * 16;
+    const unsigned char* cB_p = sB + (size_t)st * kCH * 512 + lane * 16;
+#pragma unroll
+    for (int g = 0; g < kCH / 8; ++g) {
+      const int s0 = c * kCH + g * 8;
+      tick8(s0 + 16);
+      cp_async_wait<2>();  // everything issued for steps < s0+8 has landed
+      // ---- stage this group's records in registers and validate their tags (a mismatch means a
+      // prefetch overtook its producer: rare, handled by polling the source)
+      const unsigned slot = (unsigned)(s0 & (kRD - 1));
+      float2 o2[8];
+      {
+        float4 r[8];
+        int bad = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          r[q] = *reinterpret_cast<const float4*>(sD + ((slot + q) << 9) + lane * 16);
+          bad |= __float_as_int(r[q].z) ^ tag_prev;
+        }
+        if (chk_old && bad) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (s0 + q + 2 < nsteps)
+              while (__float_as_int(r[q].z) != tag_prev) r[q] = ld_volatile4(gD + (size_t)(s0 + q + 2) * 32);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o2[q] = make_float2(r[q].x, r[q].y);
+      }
+      if (has_up && lane < 8) {  // lane q checks the record lane 0 will use at step s0+q
+        float4 r = *reinterpret_cast<const float4*>(sUp + ((slot + lane) << 4));
+        if (s0 + lane < w && __float_as_int(r.z) != tag_cur) {
+          do r = ld_volatile4(gUp + (size_t)(s0 + lane + 31 * SK) * 32); while (__float_as_int(r.z) != tag_cur);
+          *reinterpret_cast<float4*>(sUp + ((slot + lane) << 4)) = r;
+        }
+      }
+      if (chk_old && has_dn && lane >= 24) {  // lane 24+q checks the record lane 31 will use at step s0+q
+        const int iq = s0 + (lane - 24) - 31 * SK;
+        float4 r = *reinterpret_cast<const float4*>(sDn + ((slot + lane - 24) << 4));
+        if (iq >= 0 && iq < w && __float_as_int(r.z) != tag_prev) {
+          do r = ld_volatile4(gDn + (size_t)iq * 32); while (__float_as_int(r.z) != tag_prev);
+          *reinterpret_cast<float4*>(sDn + ((slot + lane - 24) << 4)) = r;
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int so = g * 8 + q;
+        const float4 cA = *reinterpret_cast<const float4*>(cA_p + so * 512);
+        const float4 cB = *reinterpret_cast<const float4*>(cB_p + so * 512);
+        const float2 old2 = o2[q];
+        float2 below = make_float2(__shfl_down_sync(FULL, (SK == 2) ? old2.x : old1.x, 1),
+                                   __shfl_down_sync(FULL, (SK == 2) ? old2.y : old1.y, 1));
+        float2 up = make_float2(__shfl_up_sync(FULL, (SK == 2) ? res2.x : res1.x, 1),
+                                __shfl_up_sync(FULL, (SK == 2) ? res2.y : res1.y, 1));
+        float vt = __shfl_up_sync(FULL, (SK == 2) ? v2 : v1, 1);
+        if (has_dn) {  // lane 31: old value of the first row of the block below
+          const float4 r = *reinterpret_cast<const float4*>(sDn + ((slot + q) << 4));
+          below.x = (lane == 31) ? r.x : below.x;
+          below.y = (lane == 31) ? r.y : below.y;
+        }
+        if (has_up) {  // lane 0: new value (this sweep) and vert weight of the last row of the block above
+          const float4 r = *reinterpret_cast<const float4*>(sUp + ((slot + q) << 4));
+          const float vv = reinterpret_cast<const float4*>(sVt + ((slot + q) << 4))->z;
+          up.x = (lane == 0) ? r.x : up.x;
+          up.y = (lane == 0) ? r.y : up.y;
+          vt = (lane == 0) ? vv : vt;
+        }
+        // ---- the reference's update (solver.c:122-131 / 180-190 / 237-247), both components.
+        // old1 is exactly 0 past the last column (inactive steps store zeros), like the reference's f2/f3.
+        float px = cA.w * old1.x, py = cA.w * old1.y;
+        const float ux = px + vt * up.x, uy = py + vt * up.y;
+        px = no_up ? px : ux;
+        py = no_up ? py : uy;
+        const float qx = px + cB.z * below.x, qy = py + cB.z * below.y;
+        px = no_dn ? px : qx;
+        py = no_dn ? py : qy;
+        const float s1 = px + cB.x, s2 = py + cB.y;
+        const float l1 = hl * res1.x + s1, l2 = hl * res1.y + s2;
+        const float B1 = (i == 0) ? s1 : l1, B2 = (i == 0) ? s2 : l2;
+        float2 nv;
+        nv.x = self_old.x + omega * (cA.x * B1 + cA.y * B2 - self_old.x);
+        nv.y = self_old.y + omega * (cA.y * B1 + cA.z * B2 - self_old.y);
+        const bool act = (unsigned)i < (unsigned)w;
+        nv.x = act ? nv.x : 0.0f;
+        nv.y = act ? nv.y : 0.0f;
+        __stcg(gOut + so * 32, make_float4(nv.x, nv.y, tagf, 0.f));
+        res2 = res1;
+        res1 = nv;
+        v2 = v1;
+        v1 = cB.z;
+        hl = cA.w;
+        self_old = old1;
+        old1 = old2;
+        ++i;
+      }
+      // ---- pacing hint for the consumers of this item (no fence: records are validated by tag)
+      if (lane == 0) *my_hint = min(s0 + 8, nsteps);
+    }
+    gOut += kCH * 32;
+    // ---- chunk consumed: refill its stage
+    __syncwarp();
+    if (lane == 0 && c + kNS < nchunks) tma_chunk(c + kNS);
+  }
+  cp_async_wait<0>();
 }
 
 // final flow = wx + du (refine_variational.cpp:212-221)
-__global__ void __launch_bounds__(256) k_update(int n, float2* __restrict__ flow, const float2* __restrict__ duv) {
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= n) return;
-  const float2 f = flow[o], d = duv[o];
+__global__ void __launch_bounds__(256) k_update(int w, int h, float2* __restrict__ flow, const float4* __restrict__ du4) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= w || j >= h) return;
+  const int o = j * w + i;
+  const float2 f = flow[o];
+  const float4 d = du4[Skew(w, h).at(i, j)];
   flow[o] = make_float2(f.x + d.x, f.y + d.y);
 }
 
 }  // namespace
 
-size_t varref_progress_ints(int h, int n_solver) { return (size_t)n_solver * ((h + 31) / 32) + 1; }
+void varref_sizes(int w, int h, int n_solver, size_t* n_coef4, size_t* n_du4, size_t* n_prog) {
+  const Skew sk(w, h);
+  *n_coef4 = (size_t)sk.K * sk.nsp * 32;
+  *n_du4 = (size_t)(sk.K + 1) * sk.nsp * 32;
+  *n_prog = (size_t)n_solver * sk.K + 2;
+}
 
 // Returns the number of kernels launched, or -1 for an unsupported level shape.
 int launch_varref(const LevelGeom& g, const VarParams& v, const float* I0, const float* I1, float2* flow,
                   const VarRefBuffers& b, cudaStream_t st, Prof* prof) {
   const int w = g.w, h = g.h, n = w * h;
-  if (w < 2 || h < 4 || v.n_solver < 1) return -1;  // reference would take its slow path / read out of range
+  if (w < 2 || h < 4 || v.n_solver < 1 || v.n_solver > 32) return -1;  // reference would take its slow path / read out of range
   int launches = 0;
   dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
   // algorithmic bytes per SURVEY.md section 8(d): warp+mask 28 B/px, derivative stack 40 B/px
@@ -422,28 +616,36 @@ int launch_varref(const LevelGeom& g, const VarParams& v, const float* I0, const
   }
   launches += 3;
   if (v.n_inner <= 0) return launches;
-  const int K = (h + 31) / 32, T = v.n_solver;
+  const Skew sk(w, h);
+  const int K = sk.K, T = v.n_solver;
+  size_t n_coef4, n_du4, n_prog;
+  varref_sizes(w, h, T, &n_coef4, &n_du4, &n_prog);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_sor_wavefront, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSorSmem);
+    attr_set = true;
+  }
+  cudaMemsetAsync(b.du4, 0, sizeof(float4) * n_du4, st);  // du = dv = 0 (image_erase, refine_variational.cpp:184-185)
   for (int it = 0; it < v.n_inner; ++it) {
-    AssembleArgs aa{w, h, v.qa, v.hg, v.hd, it == 0 ? 1 : 0, flow, b.duv, b.mask, b.Ix, b.Iy, b.Iz,
-                    b.Ixx, b.Ixy, b.Iyy, b.Ixz, b.Iyz, b.a11, b.a12, b.a22, b.b, b.hv};
+    AssembleArgs aa{w, h, v.qa, v.hg, v.hd, it == 0 ? 1 : 0, flow, b.du4,
+                    b.mask, b.Ix, b.Iy, b.Iz, b.Ixx, b.Ixy, b.Iyy, b.Ixz, b.Iyz, b.coefA, b.coefB, b.progress,
+                    T * K};
     {
       // smoothness 16 + data term 64 + sub_laplacian 32 + flow update 24 B/px
       ProfScope ps(prof, "k_assemble", g.lv, 136.0 * n);
       k_assemble<<<grid, block, 0, st>>>(aa);
     }
-    if (it == 0) cudaMemsetAsync(b.duv, 0, sizeof(float2) * n, st);
-    cudaMemsetAsync(b.progress, 0, sizeof(int) * (T * K + 1), st);
-    SorArgs sa{w, h, T, K, v.omega, b.a11, b.a12, b.a22, b.b, b.hv, b.duv, b.progress};
+    SorArgs sa{w, h, T, K, v.omega, b.coefA, b.coefB, b.du4, b.progress};
     {
       // each sweep reads 9 arrays and writes 2: 44 B/px
       ProfScope ps(prof, "k_sor_wavefront", g.lv, 44.0 * T * n);
-      k_sor_wavefront<<<T * K, 32, 0, st>>>(sa);
+      k_sor_wavefront<<<T * K, 32, kSorSmem, st>>>(sa);
     }
     launches += 2;
   }
   {
     ProfScope ps(prof, "k_update", g.lv, 8.0 * n);
-    k_update<<<(n + 255) / 256, 256, 0, st>>>(n, flow, b.duv);
+    k_update<<<grid, block, 0, st>>>(w, h, flow, b.du4);
   }
   return launches + 1;
 }
