@@ -33,6 +33,7 @@
 // dependency order, so a running warp only ever waits for warps that have already started.
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(256) k_deriv2(int w, int h, const float* __res
 }
 
 // ---- one inner fixed-point iteration: smoothness + data term + Laplacian RHS + block inverse ----
-constexpr int SK = 2;  // wavefront skew (columns per row)
+constexpr int SK = 1;  // wavefront skew (columns per row)
 
 // wavefront-major addressing of one level
 struct Skew {
@@ -296,11 +297,11 @@ struct SorArgs {
   const float4 *coefA, *coefB;  // wavefront-major [K][nsp][32]
   float4* du4;                  // wavefront-major records {du, dv, tag, -}: [K+1][nsp][32]
   int* prog;                    // [0] epoch, [1] ticket, [2 + t*K + k] pacing hint: completed steps of item (t,k)
+  int debug;                    // DIS_SOR_DEBUG=<level+1>: per-item cycle breakdown via printf (dev only)
 };
 
 constexpr int kCH = 16;       // steps per TMA chunk of the coefficient streams
 constexpr int kNS = 4;        // TMA stages in flight
-constexpr int kL = 16;        // prefetch lead (steps) of the (du,dv) record streams
 constexpr int kRD = 64;       // record ring slots (power of two > kL + 3)
 constexpr int kPublish = 8;   // pacing hint granularity (steps)
 constexpr size_t kSorSmem = (size_t)kNS * kCH * 32 * 16 * 2 + (size_t)kRD * 32 * 16 + 3 * kRD * 16 + kNS * 8;
@@ -384,6 +385,7 @@ __global__ void __launch_bounds__(32) k_sor_wavefront(const SorArgs a) {
   const int j = k * 32 + lane;
   const bool has_up = k > 0, has_dn = (k < K - 1);
   const bool no_up = (j == 0), no_dn = (j >= h - 1);
+  const bool edge_blk = (k == 0) || (k == K - 1);
   const int epoch = ld_volatile(a.prog);
   const int tag_cur = (epoch << 5) | t, tag_prev = (epoch << 5) | (t - 1);  // epoch >= 1, T <= 32
   const bool chk_old = (t > 0);                           // my old records carry the previous sweep's tag
@@ -417,10 +419,18 @@ __global__ void __launch_bounds__(32) k_sor_wavefront(const SorArgs a) {
     for (int c = 0; c < kNS && c < nchunks; ++c) tma_chunk(c);
 
   // ---- record streams in groups of 8 steps: paced by the producers' progress hints, validated by tag
+  long long c_pace = 0;
+  const long long c_all = clock64();
+  int n_pace = 0, n_bad = 0;
   auto pace = [&](const int* p, int& seen, int need) {
     need = min(need, nsteps);
     if (p && seen < need) {
+      const long long t0 = a.debug ? clock64() : 0;
       do seen = ld_volatile(p); while (seen < need);
+      if (a.debug) {
+        c_pace += clock64() - t0;
+        ++n_pace;
+      }
     }
   };
   const unsigned sD_u = smem_u32(sD) + lane * 16, sUp_u = smem_u32(sUp), sDn_u = smem_u32(sDn), sVt_u = smem_u32(sVt);
@@ -453,7 +463,6 @@ __global__ void __launch_bounds__(32) k_sor_wavefront(const SorArgs a) {
     while (__float_as_int(rec1.z) != tag_prev) rec1 = ld_volatile4(gD + 32);
   }
   tick8(0);
-  tick8(8);
 
   float2 self_old = make_float2(rec0.x, rec0.y);  // old[s]   (lane 0's first "self" is old[0])
   float2 old1 = make_float2(rec1.x, rec1.y);      // old[s+1]
@@ -473,8 +482,8 @@ __global__ void __launch_bounds__(32) k_sor_wavefront(const SorArgs a) {
 #pragma unroll
     for (int g = 0; g < kCH / 8; ++g) {
       const int s0 = c * kCH + g * 8;
-      tick8(s0 + 16);
-      cp_async_wait<2>();  // everything issued for steps < s0+8 has landed
+      tick8(s0 + 8);
+      cp_async_wait<1>();  // everything issued for steps < s0+8 has landed
       // ---- stage this group's records in registers and validate their tags (a mismatch means a
       // prefetch overtook its producer: rare, handled by polling the source)
       const unsigned slot = (unsigned)(s0 & (kRD - 1));
@@ -488,6 +497,7 @@ __global__ void __launch_bounds__(32) k_sor_wavefront(const SorArgs a) {
           bad |= __float_as_int(r[q].z) ^ tag_prev;
         }
         if (chk_old && bad) {
+          ++n_bad;
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             if (s0 + q + 2 < nsteps)
@@ -496,12 +506,12 @@ __global__ void __launch_bounds__(32) k_sor_wavefront(const SorArgs a) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) o2[q] = make_float2(r[q].x, r[q].y);
       }
-      if (has_up && lane < 8) {  // lane q checks the record lane 0 will use at step s0+q
+      if (has_up && lane < 8) {  // lane q checks the record lane 0 will use at step s0+q and adds the vert weight
         float4 r = *reinterpret_cast<const float4*>(sUp + ((slot + lane) << 4));
-        if (s0 + lane < w && __float_as_int(r.z) != tag_cur) {
+        if (s0 + lane < w && __float_as_int(r.z) != tag_cur)
           do r = ld_volatile4(gUp + (size_t)(s0 + lane + 31 * SK) * 32); while (__float_as_int(r.z) != tag_cur);
-          *reinterpret_cast<float4*>(sUp + ((slot + lane) << 4)) = r;
-        }
+        r.w = reinterpret_cast<const float4*>(sVt + ((slot + lane) << 4))->z;
+        *reinterpret_cast<float4*>(sUp + ((slot + lane) << 4)) = r;
       }
       if (chk_old && has_dn && lane >= 24) {  // lane 24+q checks the record lane 31 will use at step s0+q
         const int iq = s0 + (lane - 24) - 31 * SK;
@@ -512,56 +522,83 @@ __global__ void __launch_bounds__(32) k_sor_wavefront(const SorArgs a) {
         }
       }
       __syncwarp();
+      // ---- 8 steps.  EDGE: this block holds the first or last image row (those rows drop a term);
+      // INTERIOR: every lane is strictly inside its row for the whole group (no row start / end).
+      auto steps8 = [&](auto edge_c, auto interior_c) {
+        constexpr bool EDGE = decltype(edge_c)::value, INTERIOR = decltype(interior_c)::value;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int so = g * 8 + q;
-        const float4 cA = *reinterpret_cast<const float4*>(cA_p + so * 512);
-        const float4 cB = *reinterpret_cast<const float4*>(cB_p + so * 512);
-        const float2 old2 = o2[q];
-        float2 below = make_float2(__shfl_down_sync(FULL, (SK == 2) ? old2.x : old1.x, 1),
-                                   __shfl_down_sync(FULL, (SK == 2) ? old2.y : old1.y, 1));
-        float2 up = make_float2(__shfl_up_sync(FULL, (SK == 2) ? res2.x : res1.x, 1),
-                                __shfl_up_sync(FULL, (SK == 2) ? res2.y : res1.y, 1));
-        float vt = __shfl_up_sync(FULL, (SK == 2) ? v2 : v1, 1);
-        if (has_dn) {  // lane 31: old value of the first row of the block below
-          const float4 r = *reinterpret_cast<const float4*>(sDn + ((slot + q) << 4));
-          below.x = (lane == 31) ? r.x : below.x;
-          below.y = (lane == 31) ? r.y : below.y;
+        for (int q = 0; q < 8; ++q) {
+          const int so = g * 8 + q;
+          const float4 cA = *reinterpret_cast<const float4*>(cA_p + so * 512);
+          const float4 cB = *reinterpret_cast<const float4*>(cB_p + so * 512);
+          const float2 old2 = o2[q];
+          float2 below = make_float2(__shfl_down_sync(FULL, (SK == 2) ? old2.x : old1.x, 1),
+                                     __shfl_down_sync(FULL, (SK == 2) ? old2.y : old1.y, 1));
+          float2 up = make_float2(__shfl_up_sync(FULL, (SK == 2) ? res2.x : res1.x, 1),
+                                  __shfl_up_sync(FULL, (SK == 2) ? res2.y : res1.y, 1));
+          float vt = __shfl_up_sync(FULL, (SK == 2) ? v2 : v1, 1);
+          if (has_dn && lane == 31)  // old value of the first row of the block below
+            below = *reinterpret_cast<const float2*>(sDn + ((slot + q) << 4));
+          if (has_up && lane == 0) {  // new value (this sweep) + vert weight of the last row of the block above
+            const float4 r = *reinterpret_cast<const float4*>(sUp + ((slot + q) << 4));
+            up = make_float2(r.x, r.y);
+            vt = r.w;
+          }
+          // ---- the reference's update (solver.c:122-131 / 180-190 / 237-247), both components.
+          // old1 is exactly 0 past the last column (inactive steps store zeros), like the reference's f2/f3.
+          float px = cA.w * old1.x, py = cA.w * old1.y;
+          const float ux = px + vt * up.x, uy = py + vt * up.y;
+          if (EDGE) {
+            px = no_up ? px : ux;
+            py = no_up ? py : uy;
+          } else {
+            px = ux;
+            py = uy;
+          }
+          const float qx = px + cB.z * below.x, qy = py + cB.z * below.y;
+          if (EDGE) {
+            px = no_dn ? px : qx;
+            py = no_dn ? py : qy;
+          } else {
+            px = qx;
+            py = qy;
+          }
+          const float s1 = px + cB.x, s2 = py + cB.y;
+          const float l1 = hl * res1.x + s1, l2 = hl * res1.y + s2;
+          const float B1 = (!INTERIOR && i == 0) ? s1 : l1, B2 = (!INTERIOR && i == 0) ? s2 : l2;
+          float2 nv;
+          nv.x = self_old.x + omega * (cA.x * B1 + cA.y * B2 - self_old.x);
+          nv.y = self_old.y + omega * (cA.y * B1 + cA.z * B2 - self_old.y);
+          if (!INTERIOR) {
+            const bool act = (unsigned)i < (unsigned)w;
+            nv.x = act ? nv.x : 0.0f;
+            nv.y = act ? nv.y : 0.0f;
+            ++i;
+          }
+          __stcg(gOut + so * 32, make_float4(nv.x, nv.y, tagf, 0.f));
+          if (SK == 2) {
+            res2 = res1;
+            v2 = v1;
+          }
+          res1 = nv;
+          v1 = cB.z;
+          hl = cA.w;
+          self_old = old1;
+          old1 = old2;
         }
-        if (has_up) {  // lane 0: new value (this sweep) and vert weight of the last row of the block above
-          const float4 r = *reinterpret_cast<const float4*>(sUp + ((slot + q) << 4));
-          const float vv = reinterpret_cast<const float4*>(sVt + ((slot + q) << 4))->z;
-          up.x = (lane == 0) ? r.x : up.x;
-          up.y = (lane == 0) ? r.y : up.y;
-          vt = (lane == 0) ? vv : vt;
-        }
-        // ---- the reference's update (solver.c:122-131 / 180-190 / 237-247), both components.
-        // old1 is exactly 0 past the last column (inactive steps store zeros), like the reference's f2/f3.
-        float px = cA.w * old1.x, py = cA.w * old1.y;
-        const float ux = px + vt * up.x, uy = py + vt * up.y;
-        px = no_up ? px : ux;
-        py = no_up ? py : uy;
-        const float qx = px + cB.z * below.x, qy = py + cB.z * below.y;
-        px = no_dn ? px : qx;
-        py = no_dn ? py : qy;
-        const float s1 = px + cB.x, s2 = py + cB.y;
-        const float l1 = hl * res1.x + s1, l2 = hl * res1.y + s2;
-        const float B1 = (i == 0) ? s1 : l1, B2 = (i == 0) ? s2 : l2;
-        float2 nv;
-        nv.x = self_old.x + omega * (cA.x * B1 + cA.y * B2 - self_old.x);
-        nv.y = self_old.y + omega * (cA.y * B1 + cA.z * B2 - self_old.y);
-        const bool act = (unsigned)i < (unsigned)w;
-        nv.x = act ? nv.x : 0.0f;
-        nv.y = act ? nv.y : 0.0f;
-        __stcg(gOut + so * 32, make_float4(nv.x, nv.y, tagf, 0.f));
-        res2 = res1;
-        res1 = nv;
-        v2 = v1;
-        v1 = cB.z;
-        hl = cA.w;
-        self_old = old1;
-        old1 = old2;
-        ++i;
+        if (INTERIOR) i += 8;
+      };
+      const bool interior = (s0 > SK * 31) && (s0 + 8 <= w);
+      if (edge_blk) {
+        if (interior)
+          steps8(std::true_type{}, std::true_type{});
+        else
+          steps8(std::true_type{}, std::false_type{});
+      } else {
+        if (interior)
+          steps8(std::false_type{}, std::true_type{});
+        else
+          steps8(std::false_type{}, std::false_type{});
       }
       // ---- pacing hint for the consumers of this item (no fence: records are validated by tag)
       if (lane == 0) *my_hint = min(s0 + 8, nsteps);
@@ -572,6 +609,9 @@ __global__ void __launch_bounds__(32) k_sor_wavefront(const SorArgs a) {
     if (lane == 0 && c + kNS < nchunks) tma_chunk(c + kNS);
   }
   cp_async_wait<0>();
+  if (a.debug && lane == 0)
+    printf("sor item t=%d k=%d ticket=%d steps=%d total=%lld cyc (%.1f/step) pace=%lld (n=%d) bad_groups=%d\n", t, k, tk, nsteps,
+           clock64() - c_all, (double)(clock64() - c_all) / nsteps, c_pace, n_pace, n_bad);
 }
 
 // final flow = wx + du (refine_variational.cpp:212-221)
@@ -635,7 +675,8 @@ int launch_varref(const LevelGeom& g, const VarParams& v, const float* I0, const
       ProfScope ps(prof, "k_assemble", g.lv, 136.0 * n);
       k_assemble<<<grid, block, 0, st>>>(aa);
     }
-    SorArgs sa{w, h, T, K, v.omega, b.coefA, b.coefB, b.du4, b.progress};
+    static const int sor_debug = getenv("DIS_SOR_DEBUG") ? atoi(getenv("DIS_SOR_DEBUG")) : 0;
+    SorArgs sa{w, h, T, K, v.omega, b.coefA, b.coefB, b.du4, b.progress, sor_debug == g.lv + 1 ? 1 : 0};
     {
       // each sweep reads 9 arrays and writes 2: 44 B/px
       ProfScope ps(prof, "k_sor_wavefront", g.lv, 44.0 * T * n);
