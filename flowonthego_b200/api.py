@@ -118,6 +118,7 @@ def lib():
         L.dis_get_kernel_profile.argtypes = [vp, ctypes.POINTER(KernelTime), ip, ctypes.POINTER(ip)]
         L.dis_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
         L.dis_host_free.argtypes = [vp]
+        L.dis_read_image_gray.argtypes = [ctypes.c_char_p, vp, ctypes.c_size_t, ctypes.POINTER(ip), ctypes.POINTER(ip)]
         L.dis_write_flo.argtypes = [ctypes.c_char_p, fp, ip, ip]
         L.dis_read_flo.argtypes = [ctypes.c_char_p, fp, ctypes.c_size_t, ctypes.POINTER(ip), ctypes.POINTER(ip)]
         _LIB = L
@@ -320,18 +321,21 @@ def read_flo(path):
     return out
 
 
+def read_image_gray(path):
+    """PNG / PGM / PPM -> grey u8 (h, w), decoded natively with OpenCV's grey conversion."""
+    w, h = ctypes.c_int(), ctypes.c_int()
+    _check(lib().dis_read_image_gray(os.fsencode(path), None, 0, ctypes.byref(w), ctypes.byref(h)), None)
+    out = np.empty((h.value, w.value), np.uint8)
+    _check(lib().dis_read_image_gray(os.fsencode(path), out.ctypes.data, out.size, ctypes.byref(w), ctypes.byref(h)), None)
+    return out
+
+
 def run_dense(img1, img2, outfile, *args, device=0):
     """``run_dense img1 img2 out [X | 20 params]`` -- the reference CLI variants (kroeger/README.md:48-88).
-    img1/img2 are file names (decoded with cv2.imread(..., IMREAD_GRAYSCALE) like the reference,
-    kroeger/run_dense.cpp:208-209) or already-decoded grey u8 arrays."""
+    img1/img2 are file names (PNG/PGM/PPM, decoded natively to the same grey values as the
+    reference's cv::imread(.., GRAYSCALE), kroeger/run_dense.cpp:208-209) or decoded grey u8 arrays."""
     def load(x):
-        if isinstance(x, np.ndarray):
-            return x
-        import cv2
-        im = cv2.imread(x, cv2.IMREAD_GRAYSCALE)
-        if im is None:
-            raise DisError(4, "cannot read " + str(x))
-        return im
+        return x if isinstance(x, np.ndarray) else read_image_gray(x)
     a, b = load(img1), load(img2)
     if len(args) <= 1:
         p = Params.preset(int(args[0]) if args else 2, a.shape[1], verbosity=2)

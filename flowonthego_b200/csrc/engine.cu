@@ -21,6 +21,7 @@
 
 #include "../../include/dis_c.h"
 #include "common.cuh"
+#include "imgio.h"
 
 using namespace dis;
 
@@ -859,6 +860,23 @@ int dis_run_pyramids(dis_handle* h, const float* const* im_ao, const float* cons
   cudaEventDestroy(e3);
   if (q.verbosity > 0) printf("TIME (O.Flow Run-Time   ) (ms): %3g\n", h->tm.total_ms);
   CU(h, cudaGetLastError());
+  return DIS_OK;
+}
+
+int dis_read_image_gray(const char* path, uint8_t* out, size_t cap, int* w, int* h) {
+  if (!path || !w || !h) return DIS_ERR_INVALID_ARG;
+  GrayImage g;
+  const std::string err = read_gray_image(path, &g);
+  if (!err.empty()) {
+    g_create_error = err;
+    return DIS_ERR_IO;
+  }
+  *w = g.w;
+  *h = g.h;
+  if (out) {
+    if (cap < g.px.size()) return DIS_ERR_INVALID_ARG;
+    memcpy(out, g.px.data(), g.px.size());
+  }
   return DIS_OK;
 }
 

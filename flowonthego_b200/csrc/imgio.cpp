@@ -1,0 +1,162 @@
+#include "imgio.h"
+
+#include <zlib.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace {
+
+bool read_file(const char* path, std::vector<uint8_t>* buf) {
+  FILE* f = fopen(path, "rb");
+  if (!f) return false;
+  fseek(f, 0, SEEK_END);
+  long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  buf->resize(n > 0 ? (size_t)n : 0);
+  bool ok = n >= 0 && fread(buf->data(), 1, buf->size(), f) == buf->size();
+  fclose(f);
+  return ok;
+}
+
+// OpenCV's PxM reader -> grey (icvCvt_BGR2Gray_8u_C3C1R): (B*1868 + G*9617 + R*4899 + 8192) >> 14;
+// checked against cv2.imread(IMREAD_GRAYSCALE) of a PPM
+inline uint8_t gray_cv(int r, int g, int b) { return (uint8_t)((b * 1868 + g * 9617 + r * 4899 + 8192) >> 14); }
+// libpng png_do_rgb_to_gray as driven by OpenCV's PNG reader (png_set_rgb_to_gray(.., 0.299, 0.587)):
+// 15-bit coefficients 9797/19234/3737, truncating.  Checked bit-for-bit against
+// cv2.imread(IMREAD_GRAYSCALE) (OpenCV 4.13) on the reference's RGB frames images/alley_1/*.png.
+inline uint8_t gray_png(int r, int g, int b) { return (uint8_t)((9797 * r + 19234 * g + 3737 * b) >> 15); }
+
+std::string read_pnm(const std::vector<uint8_t>& d, GrayImage* out) {
+  size_t p = 2;
+  auto next_int = [&](int* v) {
+    while (p < d.size()) {
+      if (d[p] == '#') {
+        while (p < d.size() && d[p] != '\n') ++p;
+      } else if (d[p] == ' ' || d[p] == '\n' || d[p] == '\r' || d[p] == '\t') {
+        ++p;
+      } else {
+        break;
+      }
+    }
+    if (p >= d.size() || d[p] < '0' || d[p] > '9') return false;
+    long x = 0;
+    while (p < d.size() && d[p] >= '0' && d[p] <= '9') x = x * 10 + (d[p++] - '0');
+    *v = (int)x;
+    return true;
+  };
+  const bool color = d[1] == '6';
+  int w, h, mx;
+  if (!next_int(&w) || !next_int(&h) || !next_int(&mx)) return "bad PNM header";
+  if (mx != 255) return "only 8-bit PNM supported";
+  ++p;  // single whitespace after maxval
+  const size_t need = (size_t)w * h * (color ? 3 : 1);
+  if (w <= 0 || h <= 0 || p + need > d.size()) return "truncated PNM";
+  out->w = w;
+  out->h = h;
+  out->px.resize((size_t)w * h);
+  if (!color) {
+    memcpy(out->px.data(), d.data() + p, need);
+  } else {
+    for (size_t i = 0; i < (size_t)w * h; ++i) out->px[i] = gray_cv(d[p + 3 * i], d[p + 3 * i + 1], d[p + 3 * i + 2]);
+  }
+  return "";
+}
+
+uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+
+std::string read_png(const std::vector<uint8_t>& d, GrayImage* out) {
+  static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+  if (d.size() < 33 || memcmp(d.data(), sig, 8)) return "not a PNG";
+  size_t p = 8;
+  int w = 0, h = 0, depth = 0, ctype = 0, interlace = 0;
+  std::vector<uint8_t> idat, plte;
+  while (p + 12 <= d.size()) {
+    const uint32_t len = be32(&d[p]);
+    const char* type = (const char*)&d[p + 4];
+    if (p + 12 + len > d.size()) return "truncated PNG";
+    const uint8_t* body = &d[p + 8];
+    if (!memcmp(type, "IHDR", 4)) {
+      w = (int)be32(body);
+      h = (int)be32(body + 4);
+      depth = body[8];
+      ctype = body[9];
+      interlace = body[12];
+    } else if (!memcmp(type, "PLTE", 4)) {
+      plte.assign(body, body + len);
+    } else if (!memcmp(type, "IDAT", 4)) {
+      idat.insert(idat.end(), body, body + len);
+    } else if (!memcmp(type, "IEND", 4)) {
+      break;
+    }
+    p += 12 + len;
+  }
+  if (w <= 0 || h <= 0) return "bad PNG header";
+  if (depth != 8 || interlace != 0) return "only 8-bit non-interlaced PNG supported";
+  int ch;
+  switch (ctype) {
+    case 0: ch = 1; break;
+    case 2: ch = 3; break;
+    case 3: ch = 1; break;
+    case 4: ch = 2; break;
+    case 6: ch = 4; break;
+    default: return "unsupported PNG colour type";
+  }
+  const size_t stride = (size_t)w * ch;
+  std::vector<uint8_t> raw((stride + 1) * h);
+  uLongf rawlen = (uLongf)raw.size();
+  if (uncompress(raw.data(), &rawlen, idat.data(), (uLong)idat.size()) != Z_OK || rawlen != raw.size())
+    return "PNG inflate failed";
+  // undo the scanline filters in place
+  std::vector<uint8_t> img(stride * h);
+  for (int y = 0; y < h; ++y) {
+    const uint8_t ft = raw[(stride + 1) * y];
+    const uint8_t* src = &raw[(stride + 1) * y + 1];
+    uint8_t* cur = &img[stride * y];
+    const uint8_t* up = y ? &img[stride * (y - 1)] : nullptr;
+    for (size_t x = 0; x < stride; ++x) {
+      const int a = x >= (size_t)ch ? cur[x - ch] : 0, b = up ? up[x] : 0, c = (up && x >= (size_t)ch) ? up[x - ch] : 0;
+      int v = src[x];
+      switch (ft) {
+        case 0: break;
+        case 1: v += a; break;
+        case 2: v += b; break;
+        case 3: v += (a + b) >> 1; break;
+        case 4: {
+          const int pa = abs(b - c), pb = abs(a - c), pc = abs(a + b - 2 * c);
+          v += (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+          break;
+        }
+        default: return "bad PNG filter";
+      }
+      cur[x] = (uint8_t)v;
+    }
+  }
+  out->w = w;
+  out->h = h;
+  out->px.resize((size_t)w * h);
+  for (size_t i = 0; i < (size_t)w * h; ++i) {
+    const uint8_t* q = &img[i * ch];
+    switch (ctype) {
+      case 0: case 4: out->px[i] = q[0]; break;
+      case 2: case 6: out->px[i] = gray_png(q[0], q[1], q[2]); break;
+      case 3: {
+        if ((size_t)q[0] * 3 + 2 >= plte.size()) return "PNG palette index out of range";
+        out->px[i] = gray_png(plte[q[0] * 3], plte[q[0] * 3 + 1], plte[q[0] * 3 + 2]);
+        break;
+      }
+    }
+  }
+  return "";
+}
+
+}  // namespace
+
+std::string read_gray_image(const char* path, GrayImage* out) {
+  std::vector<uint8_t> d;
+  if (!read_file(path, &d)) return std::string("cannot read ") + path;
+  if (d.size() > 2 && d[0] == 'P' && (d[1] == '5' || d[1] == '6')) return read_pnm(d, out);
+  if (d.size() > 8 && d[0] == 0x89 && d[1] == 'P') return read_png(d, out);
+  return "unsupported image format (PNG, PGM and PPM are read natively; convert others first)";
+}

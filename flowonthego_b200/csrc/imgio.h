@@ -1,0 +1,16 @@
+// imgio.h -- minimal grey image input for the run_dense CLI: PGM/PPM (binary) and PNG (via zlib).
+// The reference reads its inputs with cv::imread(..., CV_LOAD_IMAGE_GRAYSCALE) (kroeger/run_dense.cpp:208-209);
+// OpenCV's C++ SDK is not available here, so the decode is done natively and reproduces OpenCV's
+// grey conversion (libpng's rgb_to_gray for PNG, cvtColor's fixed-point BGR2GRAY for PPM).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+struct GrayImage {
+  int w = 0, h = 0;
+  std::vector<uint8_t> px;  // row-major, pitch == w
+};
+
+// Returns empty string on success, otherwise the reason.
+std::string read_gray_image(const char* path, GrayImage* out);

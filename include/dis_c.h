@@ -155,6 +155,11 @@ int dis_write_flo(const char* path, const float* flow_uv, int w, int h);
 /* Reads the header into *w,*h; if flow_uv is non-NULL (capacity n_floats) also the data. */
 int dis_read_flo(const char* path, float* flow_uv, size_t n_floats, int* w, int* h);
 
+/* ---- image input of the CLI (kroeger/run_dense.cpp:208-209 cv::imread(.., GRAYSCALE)) ------- */
+/* Reads an 8-bit PNG / PGM / PPM as grey (OpenCV's grey conversion reproduced bit for bit).  With
+ * out == NULL only *w,*h are filled. */
+int dis_read_image_gray(const char* path, uint8_t* out, size_t cap, int* w, int* h);
+
 /* ---- stage-level debug taps (tests only; never on the timed path) ---------------------- */
 typedef enum dis_tap {
   DIS_TAP_IMG_A = 0,   /* padded pyramid image a, level l: (w_l+2p) x (h_l+2p)         */

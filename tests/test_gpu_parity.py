@@ -207,3 +207,20 @@ def test_async_and_device_entry_points():
         assert bits_differ(dflow.cpu().numpy(), ref) == 0
         t = e1.timings()
         assert t["launches"] > 10
+
+
+def test_run_dense_cli_reproduces_golden(tmp_path, golden_dir):
+    """The compiled CLI with the reference's argv grammar (kroeger/README.md:48-88) on the fixture frames."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(F.api.__file__), "run_dense")
+    a, b = os.path.join(golden_dir, "alley_0001_gray.png"), os.path.join(golden_dir, "alley_0002_gray.png")
+    golden = np.load(os.path.join(golden_dir, "alley_0001_flo.npz"))["flow"]
+    out1, out2 = str(tmp_path / "v1.flo"), str(tmp_path / "v3.flo")
+    subprocess.check_call([exe, a, b, out1])  # variant 1: operating point 2
+    argv = "5 3 12 12 0.05 0.95 0 8 0.40 0 1 0 1 10 10 5 1 3 1.6 0".split()
+    subprocess.check_call([exe, a, b, out2] + argv)  # variant 3: the same point, explicit
+    for p in (out1, out2):
+        assert os.path.getsize(p) == 3571724  # = the reference's golden file size
+        assert bits_differ(F.read_flo(p), golden) == 0
+    log = subprocess.run([exe, a, b, out1, "2"], capture_output=True, text=True).stdout
+    assert "TIME (O.Flow Run-Time   ) (ms):" in log and "TIME (Sc: 3, #p:   448" in log

@@ -81,6 +81,19 @@ def test_flo_round_trip(tmp_path):
         F.read_flo(path)
 
 
+def test_native_image_decode_matches_opencv(tmp_path, alley_pair):
+    """PNG (grey + RGB) / PGM / PPM decode == cv2.imread(IMREAD_GRAYSCALE) (kroeger/run_dense.cpp:208-209)."""
+    import cv2
+    a, _ = alley_pair
+    rgb = np.stack([a, np.roll(a, 7, 1), 255 - a], -1)[:97, :131]
+    for name, img in (("g.png", a), ("c.png", rgb), ("g.pgm", a[:50, :70]), ("c.ppm", rgb)):
+        p = str(tmp_path / name)
+        assert cv2.imwrite(p, img)
+        assert np.array_equal(F.read_image_gray(p), cv2.imread(p, cv2.IMREAD_GRAYSCALE)), name
+    with pytest.raises(F.DisError):
+        F.read_image_gray(str(tmp_path / "missing.png"))
+
+
 def test_no_cpu_fallback():
     """Without a CUDA device the engine must refuse to exist (and say why)."""
     import torch
