@@ -32,15 +32,31 @@ __device__ __forceinline__ float octet_reduce(float chain, float extra) {
   return __shfl_sync(FULL, s, 0, 8);
 }
 
+__host__ __device__ constexpr int gcd_ce(int a, int b) { return b == 0 ? a : gcd_ce(b, a % b); }
+
+// Shared-memory window of the target image per patch: every position the search may sample lies
+// within outlierthresh = p/2 of the start position (else the patch is reset to its start), so a
+// (2p+4)^2 window anchored at floor(start) - p - 1 covers all bilinear taps of all iterations.
 template <int P>
+struct Win {
+  static constexpr int W = 2 * P + 4;
+  static constexpr int STRIDE = W * W + (((W * W) % 32 == 24) ? 0 : ((24 - (W * W) % 32 + 32) % 32));  // = 24 mod 32
+};
+
+template <int P, bool L2>
 __global__ void __launch_bounds__(128) k_patch_search(const PatchSearchArgs a) {
   constexpr int N = P * P;
   constexpr int NI = N / 8;             // chain length
   constexpr bool EX = (N % 8) == 4;     // trailing packet present
   constexpr int NE = NI + (EX ? 1 : 0);
   constexpr int LB = -P / 2;
+  constexpr int M = P / gcd_ce(8, P);   // period of the (row, col) pattern of elements 8i + c
+  constexpr int ROWS = 8 * M / P;       // rows advanced per period
+  constexpr int WIN = Win<P>::W;
+  extern __shared__ float smem_win[];
 
   const int c = threadIdx.x & 7;
+  const int oct = threadIdx.x >> 3;
   int ip = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
   const bool live = ip < a.g.nop;
   if (!live) ip = a.g.nop - 1;  // dead octets shadow the last patch (shuffles stay warp-uniform)
@@ -49,18 +65,16 @@ __global__ void __launch_bounds__(128) k_patch_search(const PatchSearchArgs a) {
   const int gx = ip / a.g.noph, gy = ip - gx * a.g.noph;
   const int cx = gx * a.o.steps + a.g.offw, cy = gy * a.o.steps + a.g.offh;
 
-  // element offsets of this lane inside a patch window (row-major p x p)
-  int off[NE];
+  // element (8i + c) of the row-major patch = (row, col); the pattern repeats every M chain steps
+  int prow[M], pcol[M];
 #pragma unroll
-  for (int i = 0; i < NI; ++i) {
-    const int e = 8 * i + c;
-    off[i] = (e / P) * pitch + (e % P);
+  for (int m = 0; m < M; ++m) {
+    const int e = 8 * m + c;
+    prow[m] = e / P;
+    pcol[m] = e % P;
   }
-  if (EX) {
-    const int e = 8 * NI + (c & 3);
-    off[NE - 1] = (e / P) * pitch + (e % P);
-  }
-  const bool exl = c < 4;  // lanes holding a real tail element
+  const int te = 8 * NI + (c & 3);  // tail element (EX only)
+  const int trow = te / P, tcol = te % P;
 
   // ---- InitializePatch: template and gradients at the integer patch centre (patch.cpp:287-332)
   float T[NE], GX[NE], GY[NE];
@@ -68,9 +82,11 @@ __global__ void __launch_bounds__(128) k_patch_search(const PatchSearchArgs a) {
     const size_t base = (size_t)(cy + pad + LB) * pitch + (cx + pad + LB);
 #pragma unroll
     for (int i = 0; i < NE; ++i) {
-      T[i] = __ldg(a.I0 + base + off[i]);
-      GX[i] = __ldg(a.I0x + base + off[i]);
-      GY[i] = __ldg(a.I0y + base + off[i]);
+      const int m = i % M, k = i / M;
+      const size_t o = (i < NI) ? base + (size_t)(prow[m] + k * ROWS) * pitch + pcol[m] : base + (size_t)trow * pitch + tcol;
+      T[i] = __ldg(a.I0 + o);
+      GX[i] = __ldg(a.I0x + o);
+      GY[i] = __ldg(a.I0y + o);
     }
   }
   if (a.o.patnorm > 0) {
@@ -135,6 +151,19 @@ __global__ void __launch_bounds__(128) k_patch_search(const PatchSearchArgs a) {
     pty = (float)cy;
   }
 
+  // ---- stage the window of the target image (padded coordinates, clamped to the padded array)
+  float* win = smem_win + oct * Win<P>::STRIDE;
+  const int wx0 = (int)floorf(ptx) - P - 1 + pad, wy0 = (int)floorf(pty) - P - 1 + pad;  // window origin
+  {
+    const int tw1 = a.g.tw - 1, th1 = a.g.th - 1;
+    for (int q = c; q < WIN * WIN; q += 8) {
+      const int wy = q / WIN, wxx = q - wy * WIN;
+      const int X = min(max(wx0 + wxx, 0), tw1), Y = min(max(wy0 + wy, 0), th1);
+      win[q] = __ldg(a.I1 + (size_t)Y * pitch + X);
+    }
+  }
+  __syncwarp();
+
   float R[NE];   // |residual| per element (pweight)
   float bx = 0.0f, by = 0.0f;
   bool first = true;
@@ -174,19 +203,25 @@ __global__ void __launch_bounds__(128) k_patch_search(const PatchSearchArgs a) {
       const int posx = (int)ceilf(ptx + .00001f), posy = (int)ceilf(pty + .00001f);
       const float rx = ptx - (float)(int)floorf(ptx), ry = pty - (float)(int)floorf(pty);
       const float w0 = rx * ry, w1 = (1 - rx) * ry, w2 = rx * (1 - ry), w3 = (1 - rx) * (1 - ry);
-      const float* base = a.I1 + (size_t)(posy + pad + LB) * pitch + (posx + pad + LB);
+      // window-relative position of tap `a` of element (0,0); clamped so that no read can leave the window
+      const int ax = min(max(posx + pad + LB - wx0, 1), WIN - P), ay = min(max(posy + pad + LB - wy0, 1), WIN - P);
+      const float* wb = win + ay * WIN + ax;
+      const float* bases[M];
+#pragma unroll
+      for (int m = 0; m < M; ++m) bases[m] = wb + prow[m] * WIN + pcol[m];
+      const float* tbase = wb + trow * WIN + tcol;
       float ch = 0.0f;
 #pragma unroll
       for (int i = 0; i < NE; ++i) {
-        const float* q = base + off[i];
-        const float va = __ldg(q), vb = __ldg(q - 1), vc = __ldg(q - pitch), vd = __ldg(q - pitch - 1);
+        const float* q = (i < NI) ? bases[i % M] + (i / M) * ROWS * WIN : tbase;
+        const float va = q[0], vb = q[-1], vc = q[-WIN], vd = q[-WIN - 1];
         R[i] = w0 * va + w1 * vb + w2 * vc + w3 * vd;
         if (i == 0)
           ch = R[0];
         else if (i < NI)
           ch = ch + R[i];
       }
-      float m = 0.0f;
+      float m = 0.0f;  // x - 0.0f == x exactly, so the no-patnorm case needs no branch below
       if (a.o.patnorm > 0) m = octet_reduce<EX>(ch, EX ? R[NE - 1] : 0.0f) / (float)N;
       // LossComputeErrorImage (patch.cpp:223-262) fused with the projections of the next
       // iteration (patch.cpp:178-179) and the L1 norm of the weights (:278)
@@ -194,13 +229,13 @@ __global__ void __launch_bounds__(128) k_patch_search(const PatchSearchArgs a) {
       float egx = 0.0f, egy = 0.0f, eab = 0.0f;
 #pragma unroll
       for (int i = 0; i < NE; ++i) {
-        float d = R[i];
-        if (a.o.patnorm > 0) d = d - m;
+        float d = R[i] - m;
         d = d - T[i];
-        if (a.o.costfct == 1) {
-          d = copysignf(sqrtf(fabsf(d)), d);
-        } else if (a.o.costfct == 2) {
-          d = copysignf(sqrtf((sqrtf(1.0f + (d * d) / 25.0f) - 1.0f) * 50.0f), d);
+        if (!L2) {
+          if (a.o.costfct == 1)
+            d = copysignf(sqrtf(fabsf(d)), d);
+          else
+            d = copysignf(sqrtf((sqrtf(1.0f + (d * d) / 25.0f) - 1.0f) * 50.0f), d);
         }
         const float ad = fabsf(d);
         R[i] = ad;
@@ -237,7 +272,6 @@ __global__ void __launch_bounds__(128) k_patch_search(const PatchSearchArgs a) {
     }
     first = false;
   }
-  (void)exl;
 
   // ---- results: p_iter and the weight patch (read by AggregateFlowDense)
   if (live) {
@@ -249,22 +283,37 @@ __global__ void __launch_bounds__(128) k_patch_search(const PatchSearchArgs a) {
   }
 }
 
+template <int P>
+int launch_p(const PatchSearchArgs& a, cudaStream_t st) {
+  const int threads = 128;
+  const int blocks = (a.g.nop * 8 + threads - 1) / threads;
+  const size_t smem = (size_t)(threads / 8) * Win<P>::STRIDE * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_patch_search<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_patch_search<P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  if (a.o.costfct == 0)
+    k_patch_search<P, true><<<blocks, threads, smem, st>>>(a);
+  else
+    k_patch_search<P, false><<<blocks, threads, smem, st>>>(a);
+  return 0;
+}
+
 }  // namespace
 
 int launch_patch_search(const PatchSearchArgs& a, cudaStream_t st) {
-  const int threads = 128;
-  const int blocks = (a.g.nop * 8 + threads - 1) / threads;
   switch (a.o.p) {
-    case 4: k_patch_search<4><<<blocks, threads, 0, st>>>(a); break;
-    case 6: k_patch_search<6><<<blocks, threads, 0, st>>>(a); break;
-    case 8: k_patch_search<8><<<blocks, threads, 0, st>>>(a); break;
-    case 10: k_patch_search<10><<<blocks, threads, 0, st>>>(a); break;
-    case 12: k_patch_search<12><<<blocks, threads, 0, st>>>(a); break;
-    case 14: k_patch_search<14><<<blocks, threads, 0, st>>>(a); break;
-    case 16: k_patch_search<16><<<blocks, threads, 0, st>>>(a); break;
+    case 4: return launch_p<4>(a, st);
+    case 6: return launch_p<6>(a, st);
+    case 8: return launch_p<8>(a, st);
+    case 10: return launch_p<10>(a, st);
+    case 12: return launch_p<12>(a, st);
+    case 14: return launch_p<14>(a, st);
+    case 16: return launch_p<16>(a, st);
     default: return 1;
   }
-  return 0;
 }
 
 }  // namespace dis
