@@ -28,8 +28,9 @@ __device__ __forceinline__ float octet_reduce(float chain, float extra) {
   float r = chain + __shfl_xor_sync(FULL, chain, 4);  // p0[k] + p1[k]
   if (HAS_EXTRA) r = r + extra;                       // p0 += packet(alignedEnd2)
   const float t = r + __shfl_xor_sync(FULL, r, 2);    // r0+r2 | r1+r3
-  const float s = t + __shfl_xor_sync(FULL, t, 1);    // (r0+r2)+(r1+r3)
-  return __shfl_sync(FULL, s, 0, 8);
+  // every lane ends with the same bits: lanes c and c+4 hold equal r (a+b == b+a), the tail element is
+  // duplicated on lanes 4..7, and (r0+r2)+(r1+r3) is symmetric under the remaining swaps
+  return t + __shfl_xor_sync(FULL, t, 1);             // (r0+r2)+(r1+r3)
 }
 
 __host__ __device__ constexpr int gcd_ce(int a, int b) { return b == 0 ? a : gcd_ce(b, a % b); }
@@ -39,8 +40,10 @@ __host__ __device__ constexpr int gcd_ce(int a, int b) { return b == 0 ? a : gcd
 // (2p+4)^2 window anchored at floor(start) - p - 1 covers all bilinear taps of all iterations.
 template <int P>
 struct Win {
-  static constexpr int W = 2 * P + 4;
-  static constexpr int STRIDE = W * W + (((W * W) % 32 == 24) ? 0 : ((24 - (W * W) % 32 + 32) % 32));  // = 24 mod 32
+  // width: covers 2p+3 columns, and W - P is a multiple of 8 so that the two row segments an octet
+  // may touch in one load never share a bank (see the interleaving below)
+  static constexpr int W = P + 8 * ((P + 3 + 7) / 8);
+  static constexpr int SIZE = W * W;
 };
 
 template <int P, bool L2>
@@ -152,14 +155,26 @@ __global__ void __launch_bounds__(128) k_patch_search(const PatchSearchArgs a) {
   }
 
   // ---- stage the window of the target image (padded coordinates, clamped to the padded array)
-  float* win = smem_win + oct * Win<P>::STRIDE;
+  // The four windows of a warp are interleaved word by word (word w of octet o at 4w + o): the 8 lanes
+  // of an octet read consecutive words -> banks o, o+4, .., o+28, and the four octets occupy the four
+  // residue classes mod 4, so a warp-wide tap load is conflict-free whatever the patches' positions.
+  float* win = smem_win + (oct >> 2) * (4 * Win<P>::SIZE) + (oct & 3);
   const int wx0 = (int)floorf(ptx) - P - 1 + pad, wy0 = (int)floorf(pty) - P - 1 + pad;  // window origin
   {
+    // lane c stages columns c, c+8, c+16, ... of every window row (column clamps hoisted out of the row loop)
+    constexpr int NCOL = (WIN + 7) / 8;
     const int tw1 = a.g.tw - 1, th1 = a.g.th - 1;
-    for (int q = c; q < WIN * WIN; q += 8) {
-      const int wy = q / WIN, wxx = q - wy * WIN;
-      const int X = min(max(wx0 + wxx, 0), tw1), Y = min(max(wy0 + wy, 0), th1);
-      win[q] = __ldg(a.I1 + (size_t)Y * pitch + X);
+    int xs[NCOL];
+#pragma unroll
+    for (int u = 0; u < NCOL; ++u) xs[u] = min(max(wx0 + c + 8 * u, 0), tw1);
+    float* wrow = win + c * 4;
+#pragma unroll 4
+    for (int wy = 0; wy < WIN; ++wy) {
+      const float* src = a.I1 + (size_t)min(max(wy0 + wy, 0), th1) * pitch;
+#pragma unroll
+      for (int u = 0; u < NCOL; ++u)
+        if (c + 8 * u < WIN) wrow[32 * u] = __ldg(src + xs[u]);
+      wrow += WIN * 4;
     }
   }
   __syncwarp();
@@ -205,16 +220,16 @@ __global__ void __launch_bounds__(128) k_patch_search(const PatchSearchArgs a) {
       const float w0 = rx * ry, w1 = (1 - rx) * ry, w2 = rx * (1 - ry), w3 = (1 - rx) * (1 - ry);
       // window-relative position of tap `a` of element (0,0); clamped so that no read can leave the window
       const int ax = min(max(posx + pad + LB - wx0, 1), WIN - P), ay = min(max(posy + pad + LB - wy0, 1), WIN - P);
-      const float* wb = win + ay * WIN + ax;
+      const float* wb = win + (ay * WIN + ax) * 4;
       const float* bases[M];
 #pragma unroll
-      for (int m = 0; m < M; ++m) bases[m] = wb + prow[m] * WIN + pcol[m];
-      const float* tbase = wb + trow * WIN + tcol;
+      for (int m = 0; m < M; ++m) bases[m] = wb + (prow[m] * WIN + pcol[m]) * 4;
+      const float* tbase = wb + (trow * WIN + tcol) * 4;
       float ch = 0.0f;
 #pragma unroll
       for (int i = 0; i < NE; ++i) {
-        const float* q = (i < NI) ? bases[i % M] + (i / M) * ROWS * WIN : tbase;
-        const float va = q[0], vb = q[-1], vc = q[-WIN], vd = q[-WIN - 1];
+        const float* q = (i < NI) ? bases[i % M] + (i / M) * ROWS * WIN * 4 : tbase;
+        const float va = q[0], vb = q[-4], vc = q[-4 * WIN], vd = q[-4 * WIN - 4];
         R[i] = w0 * va + w1 * vb + w2 * vc + w3 * vd;
         if (i == 0)
           ch = R[0];
@@ -287,7 +302,7 @@ template <int P>
 int launch_p(const PatchSearchArgs& a, cudaStream_t st) {
   const int threads = 128;
   const int blocks = (a.g.nop * 8 + threads - 1) / threads;
-  const size_t smem = (size_t)(threads / 8) * Win<P>::STRIDE * sizeof(float);
+  const size_t smem = (size_t)(threads / 8) * Win<P>::SIZE * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_patch_search<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
