@@ -309,6 +309,15 @@ def main():
     ms_e = timed(lambda: step_host(), Ke)
     e2e_value = N * B * Ke / (ms_e / 1e3)
 
+    # ---- results are only *gathered* over NCCL (no data-path collective): per-pair flow summaries of the
+    # last S pairs of every rank go to rank 0
+    from flowonthego_b200 import shard
+    summ_local = {}
+    for i in range(S):
+        f = d_out[i]
+        summ_local[rank * S + i] = np.array([float(f[..., 0].mean()), float(f[..., 1].mean())], np.float32)
+    summaries = shard.gather_summaries(summ_local, world * S, dist, dev)
+
     # ---- roofline of the dominant kernel: per-kernel CUDA-event times (separate, un-graphed pass)
     roof, per_kernel = None, {}
     if rank == 0:
@@ -393,7 +402,8 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": Ke, "ms_per_step": ms_e / Ke},
                 "gpu_launches": int(launches_per_pair) * B * K, "launches_per_pair": int(launches_per_pair),
-                "clocks": clocks, "roofline": roof}
+                "clocks": clocks, "roofline": roof,
+                "gathered_summaries": None if summaries is None else int(np.isfinite(summaries).all(axis=1).sum())}
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
         if extra is not None:

@@ -532,18 +532,27 @@ __global__ void __launch_bounds__(32) k_sor_wavefront(const SorArgs a) {
           const float4 cA = *reinterpret_cast<const float4*>(cA_p + so * 512);
           const float4 cB = *reinterpret_cast<const float4*>(cB_p + so * 512);
           const float2 old2 = o2[q];
-          float2 below = make_float2(__shfl_down_sync(FULL, (SK == 2) ? old2.x : old1.x, 1),
-                                     __shfl_down_sync(FULL, (SK == 2) ? old2.y : old1.y, 1));
-          float2 up = make_float2(__shfl_up_sync(FULL, (SK == 2) ? res2.x : res1.x, 1),
-                                  __shfl_up_sync(FULL, (SK == 2) ? res2.y : res1.y, 1));
-          float vt = __shfl_up_sync(FULL, (SK == 2) ? v2 : v1, 1);
-          if (has_dn && lane == 31)  // old value of the first row of the block below
-            below = *reinterpret_cast<const float2*>(sDn + ((slot + q) << 4));
-          if (has_up && lane == 0) {  // new value (this sweep) + vert weight of the last row of the block above
-            const float4 r = *reinterpret_cast<const float4*>(sUp + ((slot + q) << 4));
-            up = make_float2(r.x, r.y);
-            vt = r.w;
+          // Neighbour rows by rotation: lane l takes "below" from lane l+1 and "up"/vt from lane l-1 (mod 32).
+          // The wrap-around sources are the hand-off records of the neighbouring row blocks: lane 0 offers
+          // the old value of the first row of the block below (read by lane 31), lane 31 offers the new
+          // value + vert weight of the last row of the block above (read by lane 0).  Their own values are
+          // not needed by anyone through these shuffles, so no branch and no extra shuffle is required.
+          float2 bsrc = (SK == 2) ? old2 : old1, usrc = (SK == 2) ? res2 : res1;
+          float vsrc = (SK == 2) ? v2 : v1;
+          if (has_dn) {
+            const float2 r = *reinterpret_cast<const float2*>(sDn + ((slot + q) << 4));
+            bsrc.x = (lane == 0) ? r.x : bsrc.x;
+            bsrc.y = (lane == 0) ? r.y : bsrc.y;
           }
+          if (has_up) {
+            const float4 r = *reinterpret_cast<const float4*>(sUp + ((slot + q) << 4));
+            usrc.x = (lane == 31) ? r.x : usrc.x;
+            usrc.y = (lane == 31) ? r.y : usrc.y;
+            vsrc = (lane == 31) ? r.w : vsrc;
+          }
+          const float2 below = make_float2(__shfl_sync(FULL, bsrc.x, (lane + 1) & 31), __shfl_sync(FULL, bsrc.y, (lane + 1) & 31));
+          const float2 up = make_float2(__shfl_sync(FULL, usrc.x, (lane + 31) & 31), __shfl_sync(FULL, usrc.y, (lane + 31) & 31));
+          const float vt = __shfl_sync(FULL, vsrc, (lane + 31) & 31);
           // ---- the reference's update (solver.c:122-131 / 180-190 / 237-247), both components.
           // old1 is exactly 0 past the last column (inactive steps store zeros), like the reference's f2/f3.
           float px = cA.w * old1.x, py = cA.w * old1.y;
