@@ -82,6 +82,9 @@ struct DensifyArgs {
   const float2* pflow_bw;   // complementary grid (forward-backward merge) or nullptr
   const float* pweight_bw;
   float2* flow;             // w*h
+  int2* anchor;             // forward-backward merge scratch: per-patch anchor,
+  float4* wbil;             //   bilinear weights,
+  int* maxdisp;             //   level-wide maximum anchor displacement
 };
 void launch_densify(const DensifyArgs& a, cudaStream_t st);
 // varref.cu

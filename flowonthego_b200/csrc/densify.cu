@@ -6,6 +6,13 @@
 // order in which the sequential splat adds to that pixel -- so the float sums are identical
 // and no atomics are needed.  Per covering patch: a = 1/max(2,|r|) (std::max(minerrval,w),
 // NaN -> 2), we += a, flow += p*a; finally flow /= we where we > 0.
+//
+// Forward-backward merging (usefbcon, patchgrid.cpp:278-375): after the forward splat the reference
+// walks the complementary grid's patches in index order and splats -flow bilinearly (weights of the
+// patch's final sub-pixel position) at the *displaced* footprint.  In gather form a pixel visits, again
+// in ascending patch index, every backward patch whose displaced footprint can reach it -- the search
+// radius comes from the largest displacement of the level (k_bw_anchors) -- and adds the up to four
+// terms cc, fc, cf, ff in the order the reference's y/x loop produces them.
 #include "common.cuh"
 
 namespace dis {
@@ -13,6 +20,27 @@ namespace {
 
 __device__ __forceinline__ float absw_of(float w) { return 1.0f / (2.0f < w ? w : 2.0f); }
 
+// Per-patch integer anchor ceil(pt_iter + 1e-5) (double arithmetic, patchgrid.cpp:304-305), bilinear
+// weights (:310-315) and the level-wide maximum anchor displacement.
+__global__ void __launch_bounds__(256) k_bw_anchors(const LevelGeom g, const OptParams o, const float2* __restrict__ pflow,
+                                                    int2* __restrict__ anchor, float4* __restrict__ wbil, int* __restrict__ maxdisp) {
+  const int ip = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= g.nop) return;
+  const int gx = ip / g.noph, gy = ip - gx * g.noph;
+  const int cx = gx * o.steps + g.offw, cy = gy * o.steps + g.offh;
+  const float2 p = pflow[ip];
+  const float rx = (float)cx + p.x, ry = (float)cy + p.y;  // GetPointPos(): pt_ref + p_iter
+  const int p0 = (int)ceil((double)rx + .00001), p1 = (int)ceil((double)ry + .00001);
+  const int p2 = (int)floor((double)rx), p3 = (int)floor((double)ry);
+  const float r0 = rx - (float)p2, r1 = ry - (float)p3;
+  anchor[ip] = make_int2(p0, p1);
+  wbil[ip] = make_float4(r0 * r1, (1 - r0) * r1, r0 * (1 - r1), (1 - r0) * (1 - r1));
+  int dsp = max(abs(p0 - cx), abs(p1 - cy));
+  dsp = min(max(dsp, 0), 1 << 14);  // NaN / overflow guard
+  atomicMax(maxdisp, dsp);          // max is order independent: deterministic
+}
+
+template <bool FB>
 __global__ void __launch_bounds__(256) k_densify(const DensifyArgs a) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -40,6 +68,41 @@ __global__ void __launch_bounds__(256) k_densify(const DensifyArgs a) {
       fv += f.y * aw;
     }
   }
+  if (FB) {
+    const int lb = -half, ub = half - 1, w = a.g.w, h = a.g.h;
+    const int D = *a.maxdisp;
+    // a patch can reach x iff its anchor p0 is in [x-ub, x-lb+1]; |p0 - centre| <= D
+    int bx0 = x - ub - D - a.g.offw, bx1 = x - lb + 1 + D - a.g.offw;
+    int by0 = y - ub - D - a.g.offh, by1 = y - lb + 1 + D - a.g.offh;
+    bx0 = bx0 <= 0 ? 0 : (bx0 + steps - 1) / steps;
+    by0 = by0 <= 0 ? 0 : (by0 + steps - 1) / steps;
+    bx1 = bx1 < 0 ? -1 : min(bx1 / steps, a.g.nopw - 1);
+    by1 = by1 < 0 ? -1 : min(by1 / steps, a.g.noph - 1);
+    for (int gx = bx0; gx <= bx1; ++gx)
+      for (int gy = by0; gy <= by1; ++gy) {
+        const int ip = gx * a.g.noph + gy;
+        const int2 an = __ldg(a.anchor + ip);
+        const int dx = x - an.x, dy = y - an.y;
+        if (dx < lb - 1 || dx > ub || dy < lb - 1 || dy > ub) continue;
+        const float2 f = __ldg(a.pflow_bw + ip);
+        const float4 wb = __ldg(a.wbil + ip);
+        const float* pw = a.pweight_bw + (size_t)ip * N;
+        // source element (ex,ey) of the patch sits at target (XT,YT) and feeds this pixel with weight wk
+        auto contrib = [&](int ex, int ey, int XT, int YT, float wk) {
+          if (ex < lb || ex > ub || ey < lb || ey > ub) return;
+          if (!(XT >= 1 && YT >= 1 && XT < (w - 1) && YT < (h - 1))) return;
+          const float aw = absw_of(__ldg(pw + (ey - lb) * P + (ex - lb)));
+          const float f0 = f.x * aw, f1 = f.y * aw;
+          we += wk * aw;
+          fu -= wk * f0;
+          fv -= wk * f1;
+        };
+        contrib(dx, dy, x, y, wb.x);              // cc
+        contrib(dx + 1, dy, x + 1, y, wb.y);      // fc
+        contrib(dx, dy + 1, x, y + 1, wb.z);      // cf
+        contrib(dx + 1, dy + 1, x + 1, y + 1, wb.w);  // ff
+      }
+  }
   float2 out = make_float2(fu, fv);
   if (we > 0.0f) {
     out.x = fu / we;
@@ -53,7 +116,13 @@ __global__ void __launch_bounds__(256) k_densify(const DensifyArgs a) {
 void launch_densify(const DensifyArgs& a, cudaStream_t st) {
   dim3 block(32, 8);
   dim3 grid((a.g.w + 31) / 32, (a.g.h + 7) / 8);
-  k_densify<<<grid, block, 0, st>>>(a);
+  if (a.pflow_bw != nullptr) {
+    cudaMemsetAsync(a.maxdisp, 0, sizeof(int), st);
+    k_bw_anchors<<<(a.g.nop + 255) / 256, 256, 0, st>>>(a.g, a.o, a.pflow_bw, a.anchor, a.wbil, a.maxdisp);
+    k_densify<true><<<grid, block, 0, st>>>(a);
+  } else {
+    k_densify<false><<<grid, block, 0, st>>>(a);
+  }
 }
 
 }  // namespace dis

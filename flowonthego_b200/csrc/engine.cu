@@ -92,6 +92,9 @@ struct dis_handle {
   uint8_t *d_a = nullptr, *d_b = nullptr;
   float2 *pflow = nullptr, *pflow_bw = nullptr;
   float *pweight = nullptr, *pweight_bw = nullptr;
+  int2* fb_anchor = nullptr;
+  float4* fb_wbil = nullptr;
+  int* fb_maxdisp = nullptr;
   VarRefBuffers vb{};
   float2* d_out = nullptr;
   Mailbox* mailbox = nullptr;
@@ -223,6 +226,9 @@ size_t carve(dis_handle* h, int w, int h_img, char* base, bool assign) {
     pflow_bw = c.take<float2>(gf.nop);
     pweight_bw = c.take<float>((size_t)gf.nop * h->opt.novals);
   }
+  int2* fb_anchor = q.usefbcon ? c.take<int2>(gf.nop) : nullptr;
+  float4* fb_wbil = q.usefbcon ? c.take<float4>(gf.nop) : nullptr;
+  int* fb_maxdisp = q.usefbcon ? c.take<int>(1) : nullptr;
   VarRefBuffers vb{};
   if (q.usetvref) {
     const size_t n = (size_t)gf.w * gf.h;
@@ -246,6 +252,9 @@ size_t carve(dis_handle* h, int w, int h_img, char* base, bool assign) {
     h->pweight = pweight;
     h->pflow_bw = pflow_bw;
     h->pweight_bw = pweight_bw;
+    h->fb_anchor = fb_anchor;
+    h->fb_wbil = fb_wbil;
+    h->fb_maxdisp = fb_maxdisp;
     h->vb = vb;
     h->d_out = d_out;
     h->w_org = w;
@@ -399,23 +408,46 @@ int enqueue_engine(dis_handle* h, const float2* d_initflow) {
       h->launches++;
       t_search = ck.stop();
     }
+    const bool fb = q.usefbcon != 0;
+    if (fb) {  // backward grid: roles of the two frames swapped (kroeger/oflow.cpp:193-197, 214-215, 234-235)
+      StageClock ck(h, &h->tm.search_ms);
+      const float2* coarse_bw = (sl < q.lv_f) ? h->lv[sl + 1].flow_bw : nullptr;
+      PatchSearchArgs pb{L.Ib, L.Ibx, L.Iby, L.Ia, L.g, h->opt, coarse_bw, h->pflow_bw, h->pweight_bw};
+      const double np_ = (double)L.g.tw * L.g.th;
+      ProfScope ps(prof, "k_patch_search", sl,
+                   16.0 * np_ + (sl < q.lv_f ? 8.0 * (double)(L.g.w / 2) * (L.g.h / 2) : 0.0) + 16.0 * L.g.nop);
+      if (launch_patch_search(pb, h->stream)) return fail(h, DIS_ERR_UNSUPPORTED, "patch size %d", h->opt.p);
+      h->launches++;
+      t_search += ck.stop();
+    }
     tap_store(h, DIS_TAP_PATCH_FLOW, sl, h->pflow, (size_t)L.g.nop * 2);
     {
       StageClock ck(h, &h->tm.densify_ms);
-      DensifyArgs da{L.g, h->opt, h->pflow, h->pweight, nullptr, nullptr, L.flow};
+      DensifyArgs da{L.g, h->opt, h->pflow, h->pweight, fb ? h->pflow_bw : nullptr, fb ? h->pweight_bw : nullptr,
+                     L.flow, h->fb_anchor, h->fb_wbil, h->fb_maxdisp};
       // SURVEY 8(d) B_A: patch results + I0,I1 in, flow out
       ProfScope ps(prof, "k_densify", sl, 16.0 * L.g.nop + 8.0 * (double)L.g.tw * L.g.th + 8.0 * (double)L.g.w * L.g.h);
       launch_densify(da, h->stream);
-      h->launches++;
+      h->launches += fb ? 2 : 1;
+      if (fb && sl > q.lv_l) {  // backward flow is only needed to seed the next finer scale (oflow.cpp:269-270)
+        DensifyArgs db{L.g, h->opt, h->pflow_bw, h->pweight_bw, h->pflow, h->pweight, L.flow_bw,
+                       h->fb_anchor, h->fb_wbil, h->fb_maxdisp};
+        launch_densify(db, h->stream);
+        h->launches += 2;
+      }
       t_dens = ck.stop();
     }
     tap_store(h, DIS_TAP_FLOW_DENSE, sl, L.flow, (size_t)L.g.w * L.g.h * 2);
     if (q.usetvref) {
       StageClock ck(h, &h->tm.varref_ms);
       vp.n_inner = q.tv_innerit * (sl + 1);  // refine_variational.cpp:36
-      const int n = launch_varref(L.g, vp, L.Ia, L.Ib, L.flow, h->vb, h->stream, prof);
+      int n = launch_varref(L.g, vp, L.Ia, L.Ib, L.flow, h->vb, h->stream, prof);
       if (n < 0) return fail(h, DIS_ERR_UNSUPPORTED, "level %d (%dx%d) too small for refinement", sl, L.g.w, L.g.h);
       h->launches += n;
+      if (fb && sl > q.lv_l) {  // oflow.cpp:291-294
+        n = launch_varref(L.g, vp, L.Ib, L.Ia, L.flow_bw, h->vb, h->stream, prof);
+        h->launches += n;
+      }
       t_var = ck.stop();
     }
     tap_store(h, DIS_TAP_FLOW_REFINED, sl, L.flow, (size_t)L.g.w * L.g.h * 2);
@@ -579,10 +611,9 @@ int dis_params_validate(const dis_params* p, char* why, size_t why_len) {
   else if (p->maxiter < 0 || p->miniter < 0) msg = "negative iteration count";
   else if (p->usetvref && p->tv_solverit < 1) msg = "tv_solverit must be >= 1";
   else if (p->usetvref && p->tv_innerit < 0) msg = "tv_innerit must be >= 0";
-  else if (p->usefbcon) msg = "usefbcon=1 (forward-backward merging) is not implemented yet";
   if (msg) {
     if (why && why_len) snprintf(why, why_len, "%s", msg);
-    return p && p->usefbcon && msg[0] == 'u' ? DIS_ERR_UNSUPPORTED : DIS_ERR_INVALID_ARG;
+    return DIS_ERR_INVALID_ARG;
   }
   if (why && why_len) why[0] = 0;
   return DIS_OK;

@@ -73,8 +73,6 @@ def test_reference_fixtures(alley_pair, golden_dir):
     for name in names:
         y0, y1, x0, x1 = z[name + "_crop"]
         pd = ref_driver.parse_params(list(z[name + "_params"]))
-        if pd["usefbcon"]:
-            continue  # SURVEY section 8(f) rank 1, not built yet
         A, B = a[y0:y1, x0:x1], b[y0:y1, x0:x1]
         with F.Engine(F.Params.from_dict(pd), A.shape[1], A.shape[0]) as e:
             e.run_u8(A, B)
@@ -82,7 +80,7 @@ def test_reference_fixtures(alley_pair, golden_dir):
         assert lvl.shape == z[name + "_flow"].shape, name
         assert bits_differ(lvl, z[name + "_flow"]) == 0, name
         ran += 1
-    assert ran >= 10
+    assert ran >= 13
 
 
 def test_stage_taps_bit_exact():
@@ -140,6 +138,17 @@ def test_cost_functions_and_patch_sizes():
             flow = e.run_u8(a, b)
         ref = port.run_u8(a, b, p.to_dict())
         assert bits_differ(flow, ref) == 0, kw
+
+
+def test_forward_backward_merging():
+    """usefbcon=1 (kroeger/patchgrid.cpp:278-375, oflow.cpp:162-170,193-197,269-294)."""
+    for (w, h, kw) in ((224, 160, dict(lv_f=2, lv_l=0)), (250, 190, dict(lv_f=3, lv_l=1, patchsz=12, poverl=0.75)),
+                       (320, 200, dict(lv_f=3, lv_l=2, usetvref=0))):
+        a, b, _ = synth_pair(w, h, seed=w + 1, shift=(6.5, -4.25), rot_deg=1.5)
+        p = params(2, w, usefbcon=1, **kw)
+        with F.Engine(p, w, h) as e:
+            flow = e.run_u8(a, b)
+        assert bits_differ(flow, port.run_u8(a, b, p.to_dict())) == 0, (w, h, kw)
 
 
 def test_ragged_and_small_inputs():
