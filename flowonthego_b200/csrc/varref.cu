@@ -301,8 +301,8 @@ struct SorArgs {
 };
 
 constexpr int kCH = 16;       // steps per TMA chunk of the coefficient streams
-constexpr int kNS = 4;        // TMA stages in flight
-constexpr int kRD = 64;       // record ring slots (power of two > kL + 3)
+constexpr int kNS = 2;        // TMA stages in flight
+constexpr int kRD = 32;       // record ring slots (power of two >= 2 groups + 2)
 constexpr int kPublish = 8;   // pacing hint granularity (steps)
 constexpr size_t kSorSmem = (size_t)kNS * kCH * 32 * 16 * 2 + (size_t)kRD * 32 * 16 + 3 * kRD * 16 + kNS * 8;
 
