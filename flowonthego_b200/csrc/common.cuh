@@ -73,6 +73,8 @@ struct PatchSearchArgs {
   float* pweight;             // nop * novals
 };
 int launch_patch_search(const PatchSearchArgs& a, cudaStream_t st);
+void patch_search_init_device();
+void varref_init_device();
 // densify.cu
 struct DensifyArgs {
   LevelGeom g;

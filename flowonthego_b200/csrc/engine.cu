@@ -665,6 +665,8 @@ int dis_create(const dis_params* params, int max_w, int max_h, int device, dis_h
     delete h;
     return DIS_ERR_CUDA;
   }
+  patch_search_init_device();
+  varref_init_device();
   rc = plan(h, max_w, max_h);
   if (rc != DIS_OK) {
     g_create_error = h->err;

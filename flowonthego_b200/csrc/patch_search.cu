@@ -303,12 +303,6 @@ int launch_p(const PatchSearchArgs& a, cudaStream_t st) {
   const int threads = 128;
   const int blocks = (a.g.nop * 8 + threads - 1) / threads;
   const size_t smem = (size_t)(threads / 8) * Win<P>::SIZE * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_patch_search<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_patch_search<P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
-  }
   if (a.o.costfct == 0)
     k_patch_search<P, true><<<blocks, threads, smem, st>>>(a);
   else
@@ -316,7 +310,25 @@ int launch_p(const PatchSearchArgs& a, cudaStream_t st) {
   return 0;
 }
 
+template <int P>
+void init_p() {
+  const int smem = (int)((128 / 8) * Win<P>::SIZE * sizeof(float));
+  cudaFuncSetAttribute(k_patch_search<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k_patch_search<P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+
 }  // namespace
+
+// per-device opt-in to > 48 KB dynamic shared memory (called from dis_create on the handle's device)
+void patch_search_init_device() {
+  init_p<4>();
+  init_p<6>();
+  init_p<8>();
+  init_p<10>();
+  init_p<12>();
+  init_p<14>();
+  init_p<16>();
+}
 
 int launch_patch_search(const PatchSearchArgs& a, cudaStream_t st) {
   switch (a.o.p) {

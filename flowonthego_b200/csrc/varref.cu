@@ -636,6 +636,9 @@ __global__ void __launch_bounds__(256) k_update(int w, int h, float2* __restrict
 
 }  // namespace
 
+// per-device opt-in to > 48 KB dynamic shared memory (called from dis_create on the handle's device)
+void varref_init_device() { cudaFuncSetAttribute(k_sor_wavefront, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSorSmem); }
+
 void varref_sizes(int w, int h, int n_solver, size_t* n_coef4, size_t* n_du4, size_t* n_prog) {
   const Skew sk(w, h);
   *n_coef4 = (size_t)sk.K * sk.nsp * 32;
@@ -669,11 +672,6 @@ int launch_varref(const LevelGeom& g, const VarParams& v, const float* I0, const
   const int K = sk.K, T = v.n_solver;
   size_t n_coef4, n_du4, n_prog;
   varref_sizes(w, h, T, &n_coef4, &n_du4, &n_prog);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_sor_wavefront, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSorSmem);
-    attr_set = true;
-  }
   cudaMemsetAsync(b.du4, 0, sizeof(float4) * n_du4, st);  // du = dv = 0 (image_erase, refine_variational.cpp:184-185)
   for (int it = 0; it < v.n_inner; ++it) {
     AssembleArgs aa{w, h, v.qa, v.hg, v.hd, it == 0 ? 1 : 0, flow, b.du4,

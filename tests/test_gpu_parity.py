@@ -197,6 +197,21 @@ def test_c4_full_size_4k_properties():
     assert bits_differ(coarse, lvl) == 0
 
 
+def test_engine_reuse_across_sizes_and_params():
+    """One handle, changing image sizes and parameter sets (re-planning drops the recorded CUDA graph)."""
+    p = params(2, 320, lv_f=3, lv_l=1)
+    with F.Engine(p, 320, 240) as e:
+        for (w, h) in ((320, 240), (200, 136), (320, 240), (352, 260)):  # the last one exceeds the create-time size
+            a, b, _ = synth_pair(w, h, seed=w + h)
+            assert bits_differ(e.run_u8(a, b), port.run_u8(a, b, p.to_dict())) == 0, (w, h)
+        p2 = p.copy(patchsz=12, poverl=0.75, lv_l=0, usetvref=0)
+        e.set_params(p2)
+        a, b, _ = synth_pair(320, 240, seed=9)
+        assert bits_differ(e.run_u8(a, b), port.run_u8(a, b, p2.to_dict())) == 0
+    with pytest.raises(F.DisError):
+        F.Engine(params(2, 64, lv_f=6, lv_l=3), 64, 48)  # coarsest level would be 1x1
+
+
 def test_async_and_device_entry_points():
     import torch
     a, b, _ = synth_pair(320, 240, seed=4)
