@@ -303,7 +303,7 @@ struct SorArgs {
 constexpr int kCH = 16;       // steps per TMA chunk of the coefficient streams
 constexpr int kNS = 2;        // TMA stages in flight
 constexpr int kRD = 32;       // record ring slots (power of two >= 2 groups + 2)
-constexpr int kPublish = 8;   // pacing hint granularity (steps)
+constexpr int kG = 16;        // steps per group: prefetch / validation / pacing-hint granularity
 constexpr size_t kSorSmem = (size_t)kNS * kCH * 32 * 16 * 2 + (size_t)kRD * 32 * 16 + 3 * kRD * 16 + kNS * 8;
 
 __device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
@@ -437,22 +437,22 @@ __global__ void __launch_bounds__(32) k_sor_wavefront(const SorArgs a) {
   // loads that steps x0..x0+7 will consume.  Addresses past a row block's end fall into the next block's
   // (allocated) storage and are never used, so nothing here is predicated on the column range.
   auto tick8 = [&](int x0) {
-    pace(p_prev, seen_prev, x0 + 7 + 2 + 1);
-    pace(p_upb, seen_upb, min(x0 + 7, w - 1) + 31 * SK + 1);
-    pace(p_dnb, seen_dnb, min(x0 + 7 - 31 * SK, w - 1) + 1);
+    pace(p_prev, seen_prev, x0 + kG - 1 + 2 + 1);
+    pace(p_upb, seen_upb, min(x0 + kG - 1, w - 1) + 31 * SK + 1);
+    pace(p_dnb, seen_dnb, min(x0 + kG - 1 - 31 * SK, w - 1) + 1);
     const unsigned slot = (unsigned)(x0 & (kRD - 1));
     const float4* src = gD + (size_t)(x0 + 2) * 32;
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
+    for (int q = 0; q < kG; ++q)
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sD_u + ((slot + q) << 9)), "l"(src + q * 32) : "memory");
-    if (lane < 8 && has_up) {  // lane q: column x0+q of the row above = block k-1, lane 31, step x0+q + 31*SK
+    if (lane < kG && has_up) {  // lane q: column x0+q of the row above = block k-1, lane 31, step x0+q + 31*SK
       const size_t o = (size_t)(x0 + lane + 31 * SK) * 32;
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sUp_u + ((slot + lane) << 4)), "l"(gUp + o) : "memory");
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sVt_u + ((slot + lane) << 4)), "l"(gVt + o) : "memory");
     }
-    if (lane >= 24 && has_dn) {  // lane 24+q: column x0+q - 31*SK of the row below = block k+1, lane 0
-      const long long o = (long long)(x0 + (lane - 24) - 31 * SK) * 32;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sDn_u + ((slot + lane - 24) << 4)), "l"(gDn + o) : "memory");
+    if (lane >= 32 - kG && has_dn) {  // lane 24+q: column x0+q - 31*SK of the row below = block k+1, lane 0
+      const long long o = (long long)(x0 + (lane - (32 - kG)) - 31 * SK) * 32;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sDn_u + ((slot + lane - (32 - kG)) << 4)), "l"(gDn + o) : "memory");
     }
     cp_async_commit();
   };
@@ -480,45 +480,45 @@ __global__ void __launch_bounds__(32) k_sor_wavefront(const SorArgs a) {
     const unsigned char* cA_p = sA + (size_t)st * kCH * 512 + lane * 16;
     const unsigned char* cB_p = sB + (size_t)st * kCH * 512 + lane * 16;
 #pragma unroll
-    for (int g = 0; g < kCH / 8; ++g) {
-      const int s0 = c * kCH + g * 8;
-      tick8(s0 + 8);
+    for (int g = 0; g < kCH / kG; ++g) {
+      const int s0 = c * kCH + g * kG;
+      tick8(s0 + kG);
       cp_async_wait<1>();  // everything issued for steps < s0+8 has landed
       // ---- stage this group's records in registers and validate their tags (a mismatch means a
       // prefetch overtook its producer: rare, handled by polling the source)
       const unsigned slot = (unsigned)(s0 & (kRD - 1));
-      float2 o2[8];
+      float2 o2[kG];
       {
-        float4 r[8];
+        float4 r[kG];
         int bad = 0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < kG; ++q) {
           r[q] = *reinterpret_cast<const float4*>(sD + ((slot + q) << 9) + lane * 16);
           bad |= __float_as_int(r[q].z) ^ tag_prev;
         }
         if (chk_old && bad) {
           ++n_bad;
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
+          for (int q = 0; q < kG; ++q)
             if (s0 + q + 2 < nsteps)
               while (__float_as_int(r[q].z) != tag_prev) r[q] = ld_volatile4(gD + (size_t)(s0 + q + 2) * 32);
         }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) o2[q] = make_float2(r[q].x, r[q].y);
+        for (int q = 0; q < kG; ++q) o2[q] = make_float2(r[q].x, r[q].y);
       }
-      if (has_up && lane < 8) {  // lane q checks the record lane 0 will use at step s0+q and adds the vert weight
+      if (has_up && lane < kG) {  // lane q checks the record lane 0 will use at step s0+q and adds the vert weight
         float4 r = *reinterpret_cast<const float4*>(sUp + ((slot + lane) << 4));
         if (s0 + lane < w && __float_as_int(r.z) != tag_cur)
           do r = ld_volatile4(gUp + (size_t)(s0 + lane + 31 * SK) * 32); while (__float_as_int(r.z) != tag_cur);
         r.w = reinterpret_cast<const float4*>(sVt + ((slot + lane) << 4))->z;
         *reinterpret_cast<float4*>(sUp + ((slot + lane) << 4)) = r;
       }
-      if (chk_old && has_dn && lane >= 24) {  // lane 24+q checks the record lane 31 will use at step s0+q
-        const int iq = s0 + (lane - 24) - 31 * SK;
-        float4 r = *reinterpret_cast<const float4*>(sDn + ((slot + lane - 24) << 4));
+      if (chk_old && has_dn && lane >= 32 - kG) {  // lane 24+q checks the record lane 31 will use at step s0+q
+        const int iq = s0 + (lane - (32 - kG)) - 31 * SK;
+        float4 r = *reinterpret_cast<const float4*>(sDn + ((slot + lane - (32 - kG)) << 4));
         if (iq >= 0 && iq < w && __float_as_int(r.z) != tag_prev) {
           do r = ld_volatile4(gDn + (size_t)iq * 32); while (__float_as_int(r.z) != tag_prev);
-          *reinterpret_cast<float4*>(sDn + ((slot + lane - 24) << 4)) = r;
+          *reinterpret_cast<float4*>(sDn + ((slot + lane - (32 - kG)) << 4)) = r;
         }
       }
       __syncwarp();
@@ -527,8 +527,8 @@ __global__ void __launch_bounds__(32) k_sor_wavefront(const SorArgs a) {
       auto steps8 = [&](auto edge_c, auto interior_c) {
         constexpr bool EDGE = decltype(edge_c)::value, INTERIOR = decltype(interior_c)::value;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int so = g * 8 + q;
+        for (int q = 0; q < kG; ++q) {
+          const int so = g * kG + q;
           const float4 cA = *reinterpret_cast<const float4*>(cA_p + so * 512);
           const float4 cB = *reinterpret_cast<const float4*>(cB_p + so * 512);
           const float2 old2 = o2[q];
@@ -595,9 +595,9 @@ __global__ void __launch_bounds__(32) k_sor_wavefront(const SorArgs a) {
           self_old = old1;
           old1 = old2;
         }
-        if (INTERIOR) i += 8;
+        if (INTERIOR) i += kG;
       };
-      const bool interior = (s0 > SK * 31) && (s0 + 8 <= w);
+      const bool interior = (s0 > SK * 31) && (s0 + kG <= w);
       if (edge_blk) {
         if (interior)
           steps8(std::true_type{}, std::true_type{});
@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(32) k_sor_wavefront(const SorArgs a) {
           steps8(std::false_type{}, std::false_type{});
       }
       // ---- pacing hint for the consumers of this item (no fence: records are validated by tag)
-      if (lane == 0) *my_hint = min(s0 + 8, nsteps);
+      if (lane == 0) *my_hint = min(s0 + kG, nsteps);
     }
     gOut += kCH * 32;
     // ---- chunk consumed: refill its stage
