@@ -159,135 +159,165 @@ struct AssembleArgs {
   int n_prog;
 };
 
-__device__ __forceinline__ float2 uu_at(const AssembleArgs& a, int i, int j) {
-  const int o = j * a.w + i;
-  const float2 f = a.flow[o];
-  if (a.first) return f;
+__device__ __forceinline__ float2 uu_at(const AssembleArgs& a, int i, int j, float2* d_out) {
+  const float2 f = a.flow[j * a.w + i];
+  if (a.first) {
+    *d_out = make_float2(0.0f, 0.0f);
+    return f;
+  }
   const float4 d = a.du4[Skew(a.w, a.h).at(i, j)];
+  *d_out = make_float2(d.x, d.y);
   return make_float2(f.x + d.x, f.y + d.y);  // refine_variational.cpp:212-213
 }
 
-// smoothness weight s(i,j), opticalflow_aux.c:128-137 with the 3-tap filters of image.c:376-399,436-464
-__device__ __forceinline__ float smooth_at(const AssembleArgs& a, int i, int j) {
-  const float c0 = -0.5f, c1 = -0.0f, c2 = 0.5f;  // deriv_flow, refine_variational.cpp:47
-  const int w = a.w, h = a.h;
-  const float2 m = uu_at(a, i, j);
-  const float2 l = uu_at(a, max(i - 1, 0), j), r = uu_at(a, min(i + 1, w - 1), j);
-  const float ux = c0 * l.x + c1 * m.x + c2 * r.x;
-  const float vx = c0 * l.y + c1 * m.y + c2 * r.y;
-  float uy, vy;
-  if (j == 0) {
-    const float2 d = uu_at(a, i, 1);
-    uy = (c0 + c1) * m.x + c2 * d.x;
-    vy = (c0 + c1) * m.y + c2 * d.y;
-  } else if (j == h - 1) {
-    const float2 u = uu_at(a, i, j - 1);
-    uy = c0 * u.x + (c1 + c2) * m.x;
-    vy = c0 * u.y + (c1 + c2) * m.y;
-  } else {
-    const float2 u = uu_at(a, i, j - 1), d = uu_at(a, i, j + 1);
-    uy = c0 * u.x + c1 * m.x + c2 * d.x;
-    vy = c0 * u.y + c1 * m.y + c2 * d.y;
-  }
-  return a.qa / sqrtf(ux * ux + uy * uy + vx * vx + vy * vy + kEps);
-}
+// Tile of 32 x 8 pixels per block.  Phase 1 stages uu = wx + du with a halo of 2 (clamped to the image,
+// which is exactly the replicate border of the reference's horizontal 3-tap filter); phase 2 computes the
+// smoothness weight s once per pixel of the tile + halo 1; phase 3 does the per-pixel assembly; phase 4
+// writes the wavefront-major coefficient streams through shared memory so that the 8 lanes of one SOR
+// step that live in this tile are written as one contiguous 128-byte run.
+constexpr int ATX = 32, ATY = 8;
 
-__global__ void __launch_bounds__(256) k_assemble(const AssembleArgs a) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+__global__ void __launch_bounds__(ATX* ATY) k_assemble(const AssembleArgs a) {
+  __shared__ float2 uu_s[ATY + 4][ATX + 4];
+  __shared__ float2 du_s[ATY][ATX];
+  __shared__ float s_s[ATY + 2][ATX + 2];
+  __shared__ float4 oa_s[ATY][ATX + 1], ob_s[ATY][ATX + 1];
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * ATX + tx;
+  const int i0 = blockIdx.x * ATX, j0 = blockIdx.y * ATY;
+  const int i = i0 + tx, j = j0 + ty;
   const int w = a.w, h = a.h;
   if (blockIdx.x == 0 && blockIdx.y == 0) {  // reset the SOR flags of the sweep that follows
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    for (int q = tid; q <= a.n_prog; q += blockDim.x * blockDim.y) a.prog[1 + q] = 0;  // ticket + counters
+    for (int q = tid; q <= a.n_prog; q += ATX * ATY) a.prog[1 + q] = 0;  // ticket + counters
     if (tid == 0) a.prog[0] += 1;  // epoch: makes the boundary tags of every launch unique
   }
-  if (i >= w || j >= h) return;
-  const int o = j * w + i;
-  // compute_smoothness: horiz(i,j) = s(i,j)+s(i+1,j) (0 for i >= w-1), vert likewise
-  const float sc = smooth_at(a, i, j);
-  const float hr = (i < w - 1) ? sc + smooth_at(a, i + 1, j) : 0.0f;
-  const float vb = (j < h - 1) ? sc + smooth_at(a, i, j + 1) : 0.0f;
-  const float hl = (i > 0) ? smooth_at(a, i - 1, j) + sc : 0.0f;
-  const float vt = (j > 0) ? smooth_at(a, i, j - 1) + sc : 0.0f;
-
-  // compute_data, 1-channel branch
-  const Skew sk(w, h);
-  float2 d = make_float2(0.0f, 0.0f);
-  if (!a.first) {
-    const float4 q = a.du4[sk.at(i, j)];
-    d = make_float2(q.x, q.y);
+  // ---- phase 1: uu (and du for the tile itself)
+  for (int q = tid; q < (ATY + 4) * (ATX + 4); q += ATX * ATY) {
+    const int ly = q / (ATX + 4), lx = q - ly * (ATX + 4);
+    const int gi = min(max(i0 + lx - 2, 0), w - 1), gj = min(max(j0 + ly - 2, 0), h - 1);
+    float2 d;
+    uu_s[ly][lx] = uu_at(a, gi, gj, &d);
+    if (lx >= 2 && lx < ATX + 2 && ly >= 2 && ly < ATY + 2) du_s[ly - 2][lx - 2] = d;
   }
-  const float du = d.x, dv = d.y;
-  const float mk = a.mask[o];
-  const float ix = a.Ix[o], iy = a.Iy[o], iz = a.Iz[o];
-  const float ixx = a.Ixx[o], ixy = a.Ixy[o], iyy = a.Iyy[o], ixz = a.Ixz[o], iyz = a.Iyz[o];
-  float A11 = 0.0f, A12 = 0.0f, A22 = 0.0f, B1 = 0.0f, B2 = 0.0f;
-  float tmp, tmp2, n1, n2;
-  if (a.hd != 0.0f) {
-    tmp = iz + ix * du + iy * dv;
-    n1 = ix * ix + iy * iy + kDnorm;
-    tmp = mk * a.hd / sqrtf(3 * tmp * tmp / n1 + kEps);
+  __syncthreads();
+  // ---- phase 2: smoothness weight s (opticalflow_aux.c:128-137; 3-tap filters image.c:376-399, 436-464)
+  for (int q = tid; q < (ATY + 2) * (ATX + 2); q += ATX * ATY) {
+    const int ly = q / (ATX + 2), lx = q - ly * (ATX + 2);
+    const int gj = j0 + ly - 1;
+    const float c0 = -0.5f, c1 = -0.0f, c2 = 0.5f;  // deriv_flow, refine_variational.cpp:47
+    const float2 m = uu_s[ly + 1][lx + 1], l = uu_s[ly + 1][lx], r = uu_s[ly + 1][lx + 2];
+    const float2 u = uu_s[ly][lx + 1], dn = uu_s[ly + 2][lx + 1];
+    const float ux = c0 * l.x + c1 * m.x + c2 * r.x;
+    const float vx = c0 * l.y + c1 * m.y + c2 * r.y;
+    float uy, vy;
+    if (gj <= 0) {
+      uy = (c0 + c1) * m.x + c2 * dn.x;
+      vy = (c0 + c1) * m.y + c2 * dn.y;
+    } else if (gj >= h - 1) {
+      uy = c0 * u.x + (c1 + c2) * m.x;
+      vy = c0 * u.y + (c1 + c2) * m.y;
+    } else {
+      uy = c0 * u.x + c1 * m.x + c2 * dn.x;
+      vy = c0 * u.y + c1 * m.y + c2 * dn.y;
+    }
+    s_s[ly][lx] = a.qa / sqrtf(ux * ux + uy * uy + vx * vx + vy * vy + kEps);
+  }
+  __syncthreads();
+  // ---- phase 3: per-pixel assembly
+  const bool inside = i < w && j < h;
+  if (inside) {
+    const int o = j * w + i;
+    // compute_smoothness: horiz(i,j) = s(i,j)+s(i+1,j) (0 for i >= w-1), vert likewise
+    const float sc = s_s[ty + 1][tx + 1];
+    const float hr = (i < w - 1) ? sc + s_s[ty + 1][tx + 2] : 0.0f;
+    const float vb = (j < h - 1) ? sc + s_s[ty + 2][tx + 1] : 0.0f;
+    const float hl = (i > 0) ? s_s[ty + 1][tx] + sc : 0.0f;
+    const float vt = (j > 0) ? s_s[ty][tx + 1] + sc : 0.0f;
+
+    // compute_data, 1-channel branch
+    const float du = du_s[ty][tx].x, dv = du_s[ty][tx].y;
+    const float mk = a.mask[o];
+    const float ix = a.Ix[o], iy = a.Iy[o], iz = a.Iz[o];
+    const float ixx = a.Ixx[o], ixy = a.Ixy[o], iyy = a.Iyy[o], ixz = a.Ixz[o], iyz = a.Iyz[o];
+    float A11 = 0.0f, A12 = 0.0f, A22 = 0.0f, B1 = 0.0f, B2 = 0.0f;
+    float tmp, tmp2, n1, n2;
+    if (a.hd != 0.0f) {
+      tmp = iz + ix * du + iy * dv;
+      n1 = ix * ix + iy * iy + kDnorm;
+      tmp = mk * a.hd / sqrtf(3 * tmp * tmp / n1 + kEps);
+      tmp /= n1;
+      A11 += tmp * ix * ix;
+      A12 += tmp * ix * iy;
+      A22 += tmp * iy * iy;
+      B1 -= tmp * iz * ix;
+      B2 -= tmp * iz * iy;
+    }
+    n1 = ixx * ixx + ixy * ixy + kDnorm;
+    n2 = iyy * iyy + ixy * ixy + kDnorm;
+    tmp = ixz + ixx * du + ixy * dv;
+    tmp2 = iyz + ixy * du + iyy * dv;
+    tmp = mk * a.hg / sqrtf(3 * tmp * tmp / n1 + 3 * tmp2 * tmp2 / n2 + kEps);
+    tmp2 = tmp / n2;
     tmp /= n1;
-    A11 += tmp * ix * ix;
-    A12 += tmp * ix * iy;
-    A22 += tmp * iy * iy;
-    B1 -= tmp * iz * ix;
-    B2 -= tmp * iz * iy;
-  }
-  n1 = ixx * ixx + ixy * ixy + kDnorm;
-  n2 = iyy * iyy + ixy * ixy + kDnorm;
-  tmp = ixz + ixx * du + ixy * dv;
-  tmp2 = iyz + ixy * du + iyy * dv;
-  tmp = mk * a.hg / sqrtf(3 * tmp * tmp / n1 + 3 * tmp2 * tmp2 / n2 + kEps);
-  tmp2 = tmp / n2;
-  tmp /= n1;
-  A11 += tmp * ixx * ixx + tmp2 * ixy * ixy;
-  A12 += tmp * ixx * ixy + tmp2 * ixy * iyy;
-  A22 += tmp2 * iyy * iyy + tmp * ixy * ixy;
-  B1 -= tmp * ixx * ixz + tmp2 * ixy * iyz;
-  B2 -= tmp2 * iyy * iyz + tmp * ixy * ixz;
-  A11 *= 3;
-  A12 *= 3;
-  A22 *= 3;
-  B1 *= 3;
-  B2 *= 3;
+    A11 += tmp * ixx * ixx + tmp2 * ixy * ixy;
+    A12 += tmp * ixx * ixy + tmp2 * ixy * iyy;
+    A22 += tmp2 * iyy * iyy + tmp * ixy * ixy;
+    B1 -= tmp * ixx * ixz + tmp2 * ixy * iyz;
+    B2 -= tmp2 * iyy * iyz + tmp * ixy * ixz;
+    A11 *= 3;
+    A12 *= 3;
+    A22 *= 3;
+    B1 *= 3;
+    B2 *= 3;
 
-  // sub_laplacian(b1, wx) and (b2, wy): horizontal pass then vertical pass, in source order
-  const float2 fc = a.flow[o];
-  if (i > 0) {
-    const float2 fl = a.flow[o - 1];
-    B1 -= hl * (fc.x - fl.x);
-    B2 -= hl * (fc.y - fl.y);
-  }
-  if (i < w - 1) {
-    const float2 fr = a.flow[o + 1];
-    B1 += hr * (fr.x - fc.x);
-    B2 += hr * (fr.y - fc.y);
-  }
-  if (j > 0) {
-    const float2 fu = a.flow[o - w];
-    B1 -= vt * (fc.x - fu.x);
-    B2 -= vt * (fc.y - fu.y);
-  }
-  if (j < h - 1) {
-    const float2 fd = a.flow[o + w];
-    B1 += vb * (fd.x - fc.x);
-    B2 += vb * (fd.y - fc.y);
-  }
+    // sub_laplacian(b1, wx) and (b2, wy): horizontal pass then vertical pass, in source order
+    const float2 fc = a.flow[o];
+    if (i > 0) {
+      const float2 fl = a.flow[o - 1];
+      B1 -= hl * (fc.x - fl.x);
+      B2 -= hl * (fc.y - fl.y);
+    }
+    if (i < w - 1) {
+      const float2 fr = a.flow[o + 1];
+      B1 += hr * (fr.x - fc.x);
+      B2 += hr * (fr.y - fc.y);
+    }
+    if (j > 0) {
+      const float2 fu = a.flow[o - w];
+      B1 -= vt * (fc.x - fu.x);
+      B2 -= vt * (fc.y - fu.y);
+    }
+    if (j < h - 1) {
+      const float2 fd = a.flow[o + w];
+      B1 += vb * (fd.x - fc.x);
+      B2 += vb * (fd.y - fc.y);
+    }
 
-  // 2x2 block inverse of sor_coupled's first sweep (solver.c:115-120, 173-178, 231-236)
-  float dpsis;
-  if (j == 0)
-    dpsis = hl + hr + vb;
-  else if (j == h - 1)
-    dpsis = hl + hr + vt;
-  else
-    dpsis = hl + hr + vt + vb;
-  const float iA11 = A22 + dpsis, iA22 = A11 + dpsis;
-  const float det = iA11 * iA22 - A12 * A12;
-  const size_t oc = sk.at(i, j);
-  a.coefA[oc] = make_float4(iA11 / det, A12 / (-det), iA22 / det, hr);
-  a.coefB[oc] = make_float4(B1, B2, vb, 0.0f);
+    // 2x2 block inverse of sor_coupled's first sweep (solver.c:115-120, 173-178, 231-236)
+    float dpsis;
+    if (j == 0)
+      dpsis = hl + hr + vb;
+    else if (j == h - 1)
+      dpsis = hl + hr + vt;
+    else
+      dpsis = hl + hr + vt + vb;
+    const float iA11 = A22 + dpsis, iA22 = A11 + dpsis;
+    const float det = iA11 * iA22 - A12 * A12;
+    oa_s[ty][tx] = make_float4(iA11 / det, A12 / (-det), iA22 / det, hr);
+    ob_s[ty][tx] = make_float4(B1, B2, vb, 0.0f);
+  }
+  __syncthreads();
+  // ---- phase 4: wavefront-major stores.  Pixels of this tile with equal tx + ty share one SOR step; their
+  // 8 lanes (rows j0..j0+7 of one 32-row block) are contiguous in the [step][lane] layout.
+  const Skew sk(w, h);
+  for (int q = tid; q < (ATX + ATY - 1) * ATY; q += ATX * ATY) {
+    const int sd = q / ATY, ry = q - sd * ATY, rx = sd - ry;
+    if (rx < 0 || rx >= ATX) continue;
+    const int gi = i0 + rx, gj = j0 + ry;
+    if (gi >= w || gj >= h) continue;
+    const size_t oc = sk.at(gi, gj);
+    a.coefA[oc] = oa_s[ry][rx];
+    a.coefB[oc] = ob_s[ry][rx];
+  }
 }
 
 // ---- sor_coupled: exact lexicographic sweeps as a skewed wavefront ------------------------------
