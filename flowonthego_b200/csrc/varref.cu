@@ -4,9 +4,9 @@
 // and the FDF1.0.1 C kernels underneath:
 //   image_warp            kroeger/FDF1.0.1/opticalflow_aux.c:18-60      -> k_warp
 //   get_derivatives       opticalflow_aux.c:65-116, image.c:401-434,466-502 -> k_deriv1, k_deriv2
-//   compute_smoothness    opticalflow_aux.c:123-165, image.c:376-399,436-464 \
-//   compute_data          opticalflow_aux.c:310-438 (1-channel branch)        > k_assemble
-//   sub_laplacian (x2)    opticalflow_aux.c:172-199                          /
+//   compute_smoothness    opticalflow_aux.c:123-165, image.c:376-399,436-464 -> k_assemble
+//   compute_data          opticalflow_aux.c:310-438 (1-channel branch)        -> k_assemble
+//   sub_laplacian (x2)    opticalflow_aux.c:172-199                          -> k_assemble
 //   sor_coupled           kroeger/FDF1.0.1/solver.c:77-421              -> k_assemble (2x2 block
 //                         inverse of the first sweep) + k_sor_wavefront (all sweeps)
 //   uu = wx+du, write-back  refine_variational.cpp:208-221, 92-99       -> k_assemble / k_update
@@ -31,8 +31,6 @@
 // (16-byte {du,dv,tag} stores, no fences); successive sweeps chase each other through coarse
 // progress counters.  Items (sweep t, row block k) are handed out through a ticket in
 // dependency order, so a running warp only ever waits for warps that have already started.
-#include <cstdio>
-#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -327,7 +325,6 @@ struct SorArgs {
   const float4 *coefA, *coefB;  // wavefront-major [K][nsp][32]
   float4* du4;                  // wavefront-major records {du, dv, tag, -}: [K+1][nsp][32]
   int* prog;                    // [0] epoch, [1] ticket, [2 + t*K + k] pacing hint: completed steps of item (t,k)
-  int debug;                    // DIS_SOR_DEBUG=<level+1>: per-item cycle breakdown via printf (dev only)
 };
 
 constexpr int kCH = 16;       // steps per TMA chunk of the coefficient streams
@@ -338,9 +335,6 @@ constexpr size_t kSorSmem = (size_t)kNS * kCH * 32 * 16 * 2 + (size_t)kRD * 32 *
 
 __device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -449,18 +443,10 @@ __global__ void __launch_bounds__(32) k_sor_wavefront(const SorArgs a) {
     for (int c = 0; c < kNS && c < nchunks; ++c) tma_chunk(c);
 
   // ---- record streams in groups of 8 steps: paced by the producers' progress hints, validated by tag
-  long long c_pace = 0;
-  const long long c_all = clock64();
-  int n_pace = 0, n_bad = 0;
   auto pace = [&](const int* p, int& seen, int need) {
     need = min(need, nsteps);
     if (p && seen < need) {
-      const long long t0 = a.debug ? clock64() : 0;
       do seen = ld_volatile(p); while (seen < need);
-      if (a.debug) {
-        c_pace += clock64() - t0;
-        ++n_pace;
-      }
     }
   };
   const unsigned sD_u = smem_u32(sD) + lane * 16, sUp_u = smem_u32(sUp), sDn_u = smem_u32(sDn), sVt_u = smem_u32(sVt);
@@ -527,7 +513,6 @@ __global__ void __launch_bounds__(32) k_sor_wavefront(const SorArgs a) {
           bad |= __float_as_int(r[q].z) ^ tag_prev;
         }
         if (chk_old && bad) {
-          ++n_bad;
 #pragma unroll
           for (int q = 0; q < kG; ++q)
             if (s0 + q + 2 < nsteps)
@@ -648,9 +633,6 @@ __global__ void __launch_bounds__(32) k_sor_wavefront(const SorArgs a) {
     if (lane == 0 && c + kNS < nchunks) tma_chunk(c + kNS);
   }
   cp_async_wait<0>();
-  if (a.debug && lane == 0)
-    printf("sor item t=%d k=%d ticket=%d steps=%d total=%lld cyc (%.1f/step) pace=%lld (n=%d) bad_groups=%d\n", t, k, tk, nsteps,
-           clock64() - c_all, (double)(clock64() - c_all) / nsteps, c_pace, n_pace, n_bad);
 }
 
 // final flow = wx + du (refine_variational.cpp:212-221)
@@ -712,8 +694,7 @@ int launch_varref(const LevelGeom& g, const VarParams& v, const float* I0, const
       ProfScope ps(prof, "k_assemble", g.lv, 136.0 * n);
       k_assemble<<<grid, block, 0, st>>>(aa);
     }
-    static const int sor_debug = getenv("DIS_SOR_DEBUG") ? atoi(getenv("DIS_SOR_DEBUG")) : 0;
-    SorArgs sa{w, h, T, K, v.omega, b.coefA, b.coefB, b.du4, b.progress, sor_debug == g.lv + 1 ? 1 : 0};
+    SorArgs sa{w, h, T, K, v.omega, b.coefA, b.coefB, b.du4, b.progress};
     {
       // each sweep reads 9 arrays and writes 2: 44 B/px
       ProfScope ps(prof, "k_sor_wavefront", g.lv, 44.0 * T * n);
