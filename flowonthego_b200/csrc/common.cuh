@@ -87,6 +87,7 @@ struct DensifyArgs {
   int2* anchor;             // forward-backward merge scratch: per-patch anchor,
   float4* wbil;             //   bilinear weights,
   int* maxdisp;             //   level-wide maximum anchor displacement
+  int cover;                // ceil(p / steps): patches covering a pixel per axis
 };
 void launch_densify(const DensifyArgs& a, cudaStream_t st);
 // varref.cu

@@ -13,6 +13,8 @@
 // in ascending patch index, every backward patch whose displaced footprint can reach it -- the search
 // radius comes from the largest displacement of the level (k_bw_anchors) -- and adds the up to four
 // terms cc, fc, cf, ff in the order the reference's y/x loop produces them.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace dis {
@@ -55,17 +57,51 @@ __global__ void __launch_bounds__(256) k_densify(const DensifyArgs a) {
   gx1 = gx1 < 0 ? -1 : min(gx1 / steps, a.g.nopw - 1);
   gy1 = gy1 < 0 ? -1 : min(gy1 / steps, a.g.noph - 1);
   float we = 0.0f, fu = 0.0f, fv = 0.0f;
-  for (int gx = gx0; gx <= gx1; ++gx) {
-    const int lx = x - (gx * steps + a.g.offw) + half;
-    for (int gy = gy0; gy <= gy1; ++gy) {
-      const int ip = gx * a.g.noph + gy;
-      const int ly = y - (gy * steps + a.g.offh) + half;
-      const float w = __ldg(a.pweight + (size_t)ip * N + ly * P + lx);
-      const float2 f = __ldg(a.pflow + ip);
-      const float aw = absw_of(w);
-      we += aw;
-      fu += f.x * aw;
-      fv += f.y * aw;
+  // common cases (p/steps <= 2 or <= 4): issue all loads first, then accumulate in patch-index order
+  auto gather_fixed = [&](auto cov_c) {
+    constexpr int C = decltype(cov_c)::value;
+    float wv[C * C];
+    float2 fl[C * C];
+    const int nx = gx1 - gx0 + 1, ny = gy1 - gy0 + 1;
+    const int lx0 = x - (gx0 * steps + a.g.offw) + half, ly0 = y - (gy0 * steps + a.g.offh) + half;
+#pragma unroll
+    for (int u = 0; u < C; ++u)
+#pragma unroll
+      for (int v = 0; v < C; ++v) {
+        const bool ok = u < nx && v < ny;
+        const int ip = ok ? (gx0 + u) * a.g.noph + gy0 + v : 0;
+        const int off = ok ? (ly0 - v * steps) * P + (lx0 - u * steps) : 0;
+        wv[u * C + v] = __ldg(a.pweight + (size_t)ip * N + off);
+        fl[u * C + v] = __ldg(a.pflow + ip);
+      }
+#pragma unroll
+    for (int u = 0; u < C; ++u)
+#pragma unroll
+      for (int v = 0; v < C; ++v)
+        if (u < nx && v < ny) {
+          const float aw = absw_of(wv[u * C + v]);
+          we += aw;
+          fu += fl[u * C + v].x * aw;
+          fv += fl[u * C + v].y * aw;
+        }
+  };
+  if (a.cover <= 2) {
+    gather_fixed(std::integral_constant<int, 2>{});
+  } else if (a.cover <= 4) {
+    gather_fixed(std::integral_constant<int, 4>{});
+  } else {
+    for (int gx = gx0; gx <= gx1; ++gx) {
+      const int lx = x - (gx * steps + a.g.offw) + half;
+      for (int gy = gy0; gy <= gy1; ++gy) {
+        const int ip = gx * a.g.noph + gy;
+        const int ly = y - (gy * steps + a.g.offh) + half;
+        const float w = __ldg(a.pweight + (size_t)ip * N + ly * P + lx);
+        const float2 f = __ldg(a.pflow + ip);
+        const float aw = absw_of(w);
+        we += aw;
+        fu += f.x * aw;
+        fv += f.y * aw;
+      }
     }
   }
   if (FB) {

@@ -424,14 +424,14 @@ int enqueue_engine(dis_handle* h, const float2* d_initflow) {
     {
       StageClock ck(h, &h->tm.densify_ms);
       DensifyArgs da{L.g, h->opt, h->pflow, h->pweight, fb ? h->pflow_bw : nullptr, fb ? h->pweight_bw : nullptr,
-                     L.flow, h->fb_anchor, h->fb_wbil, h->fb_maxdisp};
+                     L.flow, h->fb_anchor, h->fb_wbil, h->fb_maxdisp, (h->opt.p + h->opt.steps - 1) / h->opt.steps};
       // SURVEY 8(d) B_A: patch results + I0,I1 in, flow out
       ProfScope ps(prof, "k_densify", sl, 16.0 * L.g.nop + 8.0 * (double)L.g.tw * L.g.th + 8.0 * (double)L.g.w * L.g.h);
       launch_densify(da, h->stream);
       h->launches += fb ? 2 : 1;
       if (fb && sl > q.lv_l) {  // backward flow is only needed to seed the next finer scale (oflow.cpp:269-270)
         DensifyArgs db{L.g, h->opt, h->pflow_bw, h->pweight_bw, h->pflow, h->pweight, L.flow_bw,
-                       h->fb_anchor, h->fb_wbil, h->fb_maxdisp};
+                       h->fb_anchor, h->fb_wbil, h->fb_maxdisp, (h->opt.p + h->opt.steps - 1) / h->opt.steps};
         launch_densify(db, h->stream);
         h->launches += 2;
       }
