@@ -115,43 +115,51 @@ static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v
 
 /* Builds levels 0..lv_f.  I/Ix/Iy: arrays of lv_f+1 pointers, each malloc'ed here as
  * (w_l+2*pad) x (h_l+2*pad).  Ix/Iy may be NULL (no gradients). */
-ORACLE_API int oracle_build_pyramid(const uint8_t* img, int w, int h, int pitch, int lv_f, int pad,
-                                    float** I, float** Ix, float** Iy) {
-  int wp, hp, left, top, l, x, y;
+/* noc = 1: grey (SELECTCHANNEL=1); noc = 3: interleaved BGR (SELECTCHANNEL=3, run_dense.cpp:203-206).  Every
+ * OpenCV call of ConstructImgPyramide works per channel, so the colour case is the grey one on 3 planes. */
+ORACLE_API int oracle_build_pyramid_c(const uint8_t* img, int w, int h, int pitch, int noc, int lv_f, int pad,
+                                      float** I, float** Ix, float** Iy) {
+  int wp, hp, left, top, l, x, y, ch;
   float* prev = NULL;
   oracle_padded_size(w, h, lv_f, &wp, &hp, &left, &top);
   for (l = 0; l <= lv_f; ++l) {
     const int wl = wp >> l, hl = hp >> l;
-    float* cur = (float*)malloc(sizeof(float) * wl * hl);
+    float* cur = (float*)malloc(sizeof(float) * wl * hl * noc);
     if (l == 0) {
       for (y = 0; y < hl; ++y)
         for (x = 0; x < wl; ++x)
-          cur[y * wl + x] = (float)img[clampi(y - top, 0, h - 1) * pitch + clampi(x - left, 0, w - 1)];
+          for (ch = 0; ch < noc; ++ch)
+            cur[(y * wl + x) * noc + ch] =
+                (float)img[clampi(y - top, 0, h - 1) * pitch + clampi(x - left, 0, w - 1) * noc + ch];
     } else {
       const int wq = wl * 2;
       for (y = 0; y < hl; ++y)
-        for (x = 0; x < wl; ++x) {
-          const float a = prev[(2 * y) * wq + 2 * x], b = prev[(2 * y) * wq + 2 * x + 1];
-          const float c = prev[(2 * y + 1) * wq + 2 * x], d = prev[(2 * y + 1) * wq + 2 * x + 1];
-          cur[y * wl + x] = ((a + b) + (c + d)) * 0.25f;
-        }
+        for (x = 0; x < wl; ++x)
+          for (ch = 0; ch < noc; ++ch) {
+            const float a = prev[((2 * y) * wq + 2 * x) * noc + ch], b = prev[((2 * y) * wq + 2 * x + 1) * noc + ch];
+            const float c = prev[((2 * y + 1) * wq + 2 * x) * noc + ch], d = prev[((2 * y + 1) * wq + 2 * x + 1) * noc + ch];
+            cur[(y * wl + x) * noc + ch] = ((a + b) + (c + d)) * 0.25f;
+          }
     }
     {
       const int tw = wl + 2 * pad, th = hl + 2 * pad;
-      float* Ip = (float*)malloc(sizeof(float) * tw * th);
-      float* Ixp = Ix ? (float*)calloc((size_t)tw * th, sizeof(float)) : NULL;
-      float* Iyp = Iy ? (float*)calloc((size_t)tw * th, sizeof(float)) : NULL;
+      float* Ip = (float*)malloc(sizeof(float) * tw * th * noc);
+      float* Ixp = Ix ? (float*)calloc((size_t)tw * th * noc, sizeof(float)) : NULL;
+      float* Iyp = Iy ? (float*)calloc((size_t)tw * th * noc, sizeof(float)) : NULL;
       for (y = 0; y < th; ++y)
         for (x = 0; x < tw; ++x)
-          Ip[y * tw + x] = cur[clampi(y - pad, 0, hl - 1) * wl + clampi(x - pad, 0, wl - 1)];
+          for (ch = 0; ch < noc; ++ch)
+            Ip[(y * tw + x) * noc + ch] = cur[(clampi(y - pad, 0, hl - 1) * wl + clampi(x - pad, 0, wl - 1)) * noc + ch];
       if (Ixp)
         for (y = 0; y < hl; ++y)
           for (x = 0; x < wl; ++x) {
             /* reflect-101: index -1 -> 1, wl -> wl-2 */
             const int xm = x == 0 ? (wl > 1 ? 1 : 0) : x - 1, xq = x == wl - 1 ? (wl > 1 ? wl - 2 : 0) : x + 1;
             const int ym = y == 0 ? (hl > 1 ? 1 : 0) : y - 1, yq = y == hl - 1 ? (hl > 1 ? hl - 2 : 0) : y + 1;
-            Ixp[(y + pad) * tw + x + pad] = cur[y * wl + xq] - cur[y * wl + xm];
-            Iyp[(y + pad) * tw + x + pad] = cur[yq * wl + x] - cur[ym * wl + x];
+            for (ch = 0; ch < noc; ++ch) {
+              Ixp[((y + pad) * tw + x + pad) * noc + ch] = cur[(y * wl + xq) * noc + ch] - cur[(y * wl + xm) * noc + ch];
+              Iyp[((y + pad) * tw + x + pad) * noc + ch] = cur[(yq * wl + x) * noc + ch] - cur[(ym * wl + x) * noc + ch];
+            }
           }
       I[l] = Ip;
       if (Ix) Ix[l] = Ixp;
@@ -164,6 +172,11 @@ ORACLE_API int oracle_build_pyramid(const uint8_t* img, int w, int h, int pitch,
   return 0;
 }
 
+ORACLE_API int oracle_build_pyramid(const uint8_t* img, int w, int h, int pitch, int lv_f, int pad,
+                                    float** I, float** Ix, float** Iy) {
+  return oracle_build_pyramid_c(img, w, h, pitch, 1, lv_f, pad, I, Ix, Iy);
+}
+
 ORACLE_API void oracle_free(void* p) { free(p); }
 
 /* ------------------------------------------------------------------------------------------
@@ -171,7 +184,7 @@ ORACLE_API void oracle_free(void* p) { free(p); }
  * camparam (oflow.cpp:138-160, oflow.h:16-29).
  * ---------------------------------------------------------------------------------------- */
 typedef struct {
-  int p, novals, steps, max_iter, min_iter, patnorm, costfct;
+  int p, novals, steps, max_iter, min_iter, patnorm, costfct, noc;
   float outlierthresh, dp_thresh, dr_thresh, res_thresh;
 } opt_t;
 
@@ -181,7 +194,8 @@ typedef struct {
   int nopw, noph, offw, offh, nop;
 } lvl_t;
 
-static void make_opt(const dis_params* q, opt_t* o) {
+static void make_opt(const dis_params* q, int noc, opt_t* o) {
+  o->noc = noc;
   o->p = q->patchsz;
   o->outlierthresh = (float)o->p / 2;
   o->max_iter = q->maxiter;
@@ -193,7 +207,7 @@ static void make_opt(const dis_params* q, opt_t* o) {
     int s = (int)floor(o->p * (1 - q->poverl)); /* oflow.cpp:91: int*float -> float, floor(double) */
     o->steps = s > 1 ? s : 1;
   }
-  o->novals = o->p * o->p;
+  o->novals = noc * o->p * o->p; /* oflow.cpp:92 */
   o->patnorm = q->patnorm;
   o->costfct = q->costfct;
 }
@@ -231,10 +245,14 @@ static void patch_bilinear(const float* img, const lvl_t* c, const opt_t* o, flo
   posx += c->pad;
   posy += c->pad;
   for (y = posy + lb; y <= posy + ub; ++y)
-    for (x = posx + lb; x <= posx + ub; ++x, ++k) {
-      const float a = img[y * c->tmp_w + x], b = img[y * c->tmp_w + x - 1];
-      const float cc = img[(y - 1) * c->tmp_w + x], d = img[(y - 1) * c->tmp_w + x - 1];
-      out[k] = w0 * a + w1 * b + w2 * cc + w3 * d;
+    for (x = posx + lb; x <= posx + ub; ++x) {
+      int ch;
+      for (ch = 0; ch < o->noc; ++ch, ++k) { /* RGB: 3 interleaved channels, same weights (patch.cpp:392-396) */
+        const int n = o->noc;
+        const float a = img[(y * c->tmp_w + x) * n + ch], b = img[(y * c->tmp_w + x - 1) * n + ch];
+        const float cc = img[((y - 1) * c->tmp_w + x) * n + ch], d = img[((y - 1) * c->tmp_w + x - 1) * n + ch];
+        out[k] = w0 * a + w1 * b + w2 * cc + w3 * d;
+      }
     }
   if (o->patnorm > 0) {
     const float m = eig_sum(out, o->novals) / o->novals;
@@ -296,11 +314,14 @@ static void patch_run(const float* ima, const float* imax, const float* imay, co
   int i, j, k = 0;
   const int px = cx + c->pad, py = cy + c->pad;
   for (j = lb; j <= ub; ++j)
-    for (i = lb; i <= ub; ++i, ++k) {
-      const int idx = (px + i) + (py + j) * c->tmp_w;
-      tmpl[k] = ima[idx];
-      gx[k] = imax[idx];
-      gy[k] = imay[idx];
+    for (i = lb; i <= ub; ++i) {
+      int ch;
+      for (ch = 0; ch < o->noc; ++ch, ++k) { /* patch.cpp:316-325 */
+        const int idx = ((px + i) + (py + j) * c->tmp_w) * o->noc + ch;
+        tmpl[k] = ima[idx];
+        gx[k] = imax[idx];
+        gy[k] = imay[idx];
+      }
     }
   if (o->patnorm > 0) {
     const float m = eig_sum(tmpl, n) / n;
@@ -383,6 +404,17 @@ ORACLE_API void oracle_grid_search(const float* ima, const float* imax, const fl
   free(scratch);
 }
 
+/* pixel weight, kroeger/patchgrid.cpp:253-260 (and :330-337) */
+static float patch_absw(const opt_t* o, const float* pw) {
+  if (o->noc == 1) return 1.0f / (2.0f < pw[0] ? pw[0] : 2.0f);
+  {
+    float a = (2.0f < pw[0] ? pw[0] : 2.0f);
+    a += (2.0f < pw[1] ? pw[1] : 2.0f);
+    a += (2.0f < pw[2] ? pw[2] : 2.0f);
+    return 1.0f / a;
+  }
+}
+
 /* A1: AggregateFlowDense, kroeger/patchgrid.cpp:213-397.
  * pt_bw/pflow_bw/pweight_bw (complementary grid, forward-backward merge :278-375) may be NULL;
  * ptpos_bw holds the backward patches' final positions pt_iter. */
@@ -397,12 +429,16 @@ ORACLE_API void oracle_densify(const lvl_t* c, const opt_t* o, const float* pflo
       const int ip = gx * c->noph + gy;
       const float* pw = pweight + (size_t)ip * o->novals;
       const float cx = (float)(gx * o->steps + c->offw), cy = (float)(gy * o->steps + c->offh);
+      /* RGB quirk of the reference (patchgrid.cpp:241-260): the weight pointer advances by 3 only for pixels
+       * inside the image and by 1 for skipped ones, so after a skipped pixel the channels are misaligned.
+       * Reproduced as is. */
       for (y = lb; y <= ub; ++y)
         for (x = lb; x <= ub; ++x, ++pw) {
           const int yt = (int)(y + cy), xt = (int)(x + cx);
           if (xt >= 0 && yt >= 0 && xt < w && yt < h) {
             const int i = yt * w + xt;
-            const float absw = 1.0f / (2.0f < *pw ? *pw : 2.0f); /* std::max(minerrval,*pweight) */
+            const float absw = patch_absw(o, pw); /* std::max(minerrval,*pweight) */
+            pw += o->noc - 1;
             const float f0 = pflow[2 * ip] * absw, f1 = pflow[2 * ip + 1] * absw;
             we[i] += absw;
             flowout[2 * i] += f0;
@@ -424,10 +460,11 @@ ORACLE_API void oracle_densify(const lvl_t* c, const opt_t* o, const float* pflo
         const float r0 = rx - p2, r1 = ry - p3;
         const float wb0 = r0 * r1, wb1 = (1 - r0) * r1, wb2 = r0 * (1 - r1), wb3 = (1 - r0) * (1 - r1);
         for (y = lb; y <= ub; ++y)
-          for (x = lb; x <= ub; ++x, ++pw) {
+          for (x = lb; x <= ub; ++x, ++pw) { /* same pointer quirk as above (patchgrid.cpp:321-337) */
             const int yt = y + p1, xt = x + p0;
             if (xt >= 1 && yt >= 1 && xt < (w - 1) && yt < (h - 1)) {
-              const float absw = 1.0f / (2.0f < *pw ? *pw : 2.0f);
+              const float absw = patch_absw(o, pw);
+              pw += o->noc - 1;
               const float f0 = pflow_bw[2 * ip] * absw, f1 = pflow_bw[2 * ip + 1] * absw;
               const int cc = xt + yt * w, fc = (xt - 1) + yt * w, cf = xt + (yt - 1) * w, ff = (xt - 1) + (yt - 1) * w;
               we[cc] += wb0 * absw;
@@ -525,29 +562,37 @@ static void deriv_coeffs(float* cf5, float* cf3) {
 #define MINMAX_TA(a, b) ((((a) > 0 ? (a) : 0)) < ((b)-1) ? ((a) > 0 ? (a) : 0) : ((b)-1))
 
 ORACLE_API void oracle_varref(const float* ima_pad, const float* imb_pad, const lvl_t* c,
-                              const dis_params* q, float* flow) {
+                              const dis_params* q, int noc, float* flow) {
   const int w = c->w, h = c->h, n = w * h;
   const int n_inner = q->tv_innerit * (c->lv + 1); /* refine_variational.cpp:36 */
   const float qa = 0.25f * q->tv_alpha, hg = q->tv_gamma * 0.5f / 3.0f, hd = q->tv_delta * 0.5f / 3.0f;
   const float omega = q->tv_sor;
   const float dnorm = 0.1f * 0.1f, eps = 0.001f * 0.001f; /* opticalflow_aux.c:10-14 */
   float cf5[5], cf3[3];
-  float* buf = (float*)calloc((size_t)n * 32, sizeof(float));
-  float *wx = buf, *wy = buf + n, *im1 = buf + 2 * n, *im2 = buf + 3 * n, *du = buf + 4 * n, *dv = buf + 5 * n;
-  float *mask = buf + 6 * n, *sh = buf + 7 * n, *sv = buf + 8 * n, *uu = buf + 9 * n, *vv = buf + 10 * n;
-  float *a11 = buf + 11 * n, *a12 = buf + 12 * n, *a22 = buf + 13 * n, *b1 = buf + 14 * n, *b2 = buf + 15 * n;
-  float *wim = buf + 16 * n, *Ix = buf + 17 * n, *Iy = buf + 18 * n, *Iz = buf + 19 * n, *Ixx = buf + 20 * n;
-  float *Ixy = buf + 21 * n, *Iyy = buf + 22 * n, *Ixz = buf + 23 * n, *Iyz = buf + 24 * n, *avg = buf + 25 * n;
-  float *ux = buf + 26 * n, *uy = buf + 27 * n, *vx = buf + 28 * n, *vy = buf + 29 * n, *sm = buf + 30 * n;
-  int i, j, k, it, iter;
+  float* buf = (float*)calloc((size_t)n * (20 + 12 * noc), sizeof(float));
+  float *wx = buf, *wy = buf + n, *du = buf + 2 * n, *dv = buf + 3 * n;
+  float *mask = buf + 4 * n, *sh = buf + 5 * n, *sv = buf + 6 * n, *uu = buf + 7 * n, *vv = buf + 8 * n;
+  float *a11 = buf + 9 * n, *a12 = buf + 10 * n, *a22 = buf + 11 * n, *b1 = buf + 12 * n, *b2 = buf + 13 * n;
+  float *ux = buf + 14 * n, *uy = buf + 15 * n, *vx = buf + 16 * n, *vy = buf + 17 * n, *sm = buf + 18 * n;
+  /* per-channel planes (color_image_t: c1, c2, c3), 12 each */
+  float *im1[3], *im2[3], *wim[3], *avg[3], *Ix[3], *Iy[3], *Iz[3], *Ixx[3], *Ixy[3], *Iyy[3], *Ixz[3], *Iyz[3];
+  int i, j, k, it, iter, ch;
+  for (ch = 0; ch < noc; ++ch) {
+    float* pch = buf + (size_t)(20 + 12 * ch) * n;
+    im1[ch] = pch; im2[ch] = pch + n; wim[ch] = pch + 2 * n; avg[ch] = pch + 3 * n; Ix[ch] = pch + 4 * n;
+    Iy[ch] = pch + 5 * n; Iz[ch] = pch + 6 * n; Ixx[ch] = pch + 7 * n; Ixy[ch] = pch + 8 * n; Iyy[ch] = pch + 9 * n;
+    Ixz[ch] = pch + 10 * n; Iyz[ch] = pch + 11 * n;
+  }
   deriv_coeffs(cf5, cf3);
-  /* refine_variational.cpp:61-82, copyimage :120-149 */
+  /* refine_variational.cpp:61-82, copyimage :120-149 (de-interleaves the colour channels) */
   for (j = 0; j < h; ++j)
     for (i = 0; i < w; ++i) {
       wx[j * w + i] = flow[2 * (j * w + i)];
       wy[j * w + i] = flow[2 * (j * w + i) + 1];
-      im1[j * w + i] = ima_pad[(j + c->pad) * c->tmp_w + i + c->pad];
-      im2[j * w + i] = imb_pad[(j + c->pad) * c->tmp_w + i + c->pad];
+      for (ch = 0; ch < noc; ++ch) {
+        im1[ch][j * w + i] = ima_pad[((j + c->pad) * c->tmp_w + i + c->pad) * noc + ch];
+        im2[ch][j * w + i] = imb_pad[((j + c->pad) * c->tmp_w + i + c->pad) * noc + ch];
+      }
     }
   /* image_warp, opticalflow_aux.c:18-60 */
   for (j = 0; j < h; ++j)
@@ -558,21 +603,26 @@ ORACLE_API void oracle_varref(const float* ima_pad, const float* imb_pad, const 
       const float dx = xx - x, dy = yy - y;
       const int x1 = MINMAX_TA(x, w), x2 = MINMAX_TA(x + 1, w), y1 = MINMAX_TA(y, h), y2 = MINMAX_TA(y + 1, h);
       mask[o] = (xx >= 0 && xx <= w - 1 && yy >= 0 && yy <= h - 1);
-      wim[o] = im2[y1 * w + x1] * (1.0f - dx) * (1.0f - dy) + im2[y1 * w + x2] * dx * (1.0f - dy) +
-               im2[y2 * w + x1] * (1.0f - dx) * dy + im2[y2 * w + x2] * dx * dy;
+      for (ch = 0; ch < noc; ++ch) {
+        const float* s2 = im2[ch];
+        wim[ch][o] = s2[y1 * w + x1] * (1.0f - dx) * (1.0f - dy) + s2[y1 * w + x2] * dx * (1.0f - dy) +
+                     s2[y2 * w + x1] * (1.0f - dx) * dy + s2[y2 * w + x2] * dx * dy;
+      }
     }
   /* get_derivatives, opticalflow_aux.c:65-116 */
-  for (k = 0; k < n; ++k) {
-    avg[k] = 0.5f * (wim[k] + im1[k]);
-    Iz[k] = wim[k] - im1[k];
+  for (ch = 0; ch < noc; ++ch) {
+    for (k = 0; k < n; ++k) {
+      avg[ch][k] = 0.5f * (wim[ch][k] + im1[ch][k]);
+      Iz[ch][k] = wim[ch][k] - im1[ch][k];
+    }
+    conv_h(Ix[ch], avg[ch], w, h, cf5, 2);
+    conv_v(Iy[ch], avg[ch], w, h, cf5, 2);
+    conv_h(Ixx[ch], Ix[ch], w, h, cf5, 2);
+    conv_v(Ixy[ch], Ix[ch], w, h, cf5, 2);
+    conv_v(Iyy[ch], Iy[ch], w, h, cf5, 2);
+    conv_h(Ixz[ch], Iz[ch], w, h, cf5, 2);
+    conv_v(Iyz[ch], Iz[ch], w, h, cf5, 2);
   }
-  conv_h(Ix, avg, w, h, cf5, 2);
-  conv_v(Iy, avg, w, h, cf5, 2);
-  conv_h(Ixx, Ix, w, h, cf5, 2);
-  conv_v(Ixy, Ix, w, h, cf5, 2);
-  conv_v(Iyy, Iy, w, h, cf5, 2);
-  conv_h(Ixz, Iz, w, h, cf5, 2);
-  conv_v(Iyz, Iz, w, h, cf5, 2);
   /* refine_variational.cpp:184-189: du = dv = 0 (calloc), uu = wx, vv = wy */
   memcpy(uu, wx, sizeof(float) * n);
   memcpy(vv, wy, sizeof(float) * n);
@@ -589,38 +639,79 @@ ORACLE_API void oracle_varref(const float* ima_pad, const float* imb_pad, const 
         sh[j * w + i] = (i < w - 1) ? sm[j * w + i] + sm[j * w + i + 1] : 0.0f;
         sv[j * w + i] = (j < h - 1) ? sm[j * w + i] + sm[(j + 1) * w + i] : 0.0f;
       }
-    /* compute_data, single channel, opticalflow_aux.c:310-438 */
+    /* compute_data, opticalflow_aux.c:310-438 */
     for (k = 0; k < n; ++k) {
-      float tmp, tmp2, n1, n2;
       float A11 = 0.0f, A12 = 0.0f, A22 = 0.0f, B1 = 0.0f, B2 = 0.0f;
-      if (hd) {
-        tmp = Iz[k] + Ix[k] * du[k] + Iy[k] * dv[k];
-        n1 = Ix[k] * Ix[k] + Iy[k] * Iy[k] + dnorm;
-        tmp = mask[k] * hd / sqrtf(3 * tmp * tmp / n1 + eps);
+      if (noc == 1) { /* single channel branch */
+        float tmp, tmp2, n1, n2;
+        const float *ix = Ix[0], *iy = Iy[0], *iz = Iz[0], *ixx = Ixx[0], *ixy = Ixy[0], *iyy = Iyy[0], *ixz = Ixz[0], *iyz = Iyz[0];
+        if (hd) {
+          tmp = iz[k] + ix[k] * du[k] + iy[k] * dv[k];
+          n1 = ix[k] * ix[k] + iy[k] * iy[k] + dnorm;
+          tmp = mask[k] * hd / sqrtf(3 * tmp * tmp / n1 + eps);
+          tmp /= n1;
+          A11 += tmp * ix[k] * ix[k];
+          A12 += tmp * ix[k] * iy[k];
+          A22 += tmp * iy[k] * iy[k];
+          B1 -= tmp * iz[k] * ix[k];
+          B2 -= tmp * iz[k] * iy[k];
+        }
+        n1 = ixx[k] * ixx[k] + ixy[k] * ixy[k] + dnorm;
+        n2 = iyy[k] * iyy[k] + ixy[k] * ixy[k] + dnorm;
+        tmp = ixz[k] + ixx[k] * du[k] + ixy[k] * dv[k];
+        tmp2 = iyz[k] + ixy[k] * du[k] + iyy[k] * dv[k];
+        tmp = mask[k] * hg / sqrtf(3 * tmp * tmp / n1 + 3 * tmp2 * tmp2 / n2 + eps);
+        tmp2 = tmp / n2;
         tmp /= n1;
-        A11 += tmp * Ix[k] * Ix[k];
-        A12 += tmp * Ix[k] * Iy[k];
-        A22 += tmp * Iy[k] * Iy[k];
-        B1 -= tmp * Iz[k] * Ix[k];
-        B2 -= tmp * Iz[k] * Iy[k];
+        A11 += tmp * ixx[k] * ixx[k] + tmp2 * ixy[k] * ixy[k];
+        A12 += tmp * ixx[k] * ixy[k] + tmp2 * ixy[k] * iyy[k];
+        A22 += tmp2 * iyy[k] * iyy[k] + tmp * ixy[k] * ixy[k];
+        B1 -= tmp * ixx[k] * ixz[k] + tmp2 * ixy[k] * iyz[k];
+        B2 -= tmp2 * iyy[k] * iyz[k] + tmp * ixy[k] * ixz[k];
+        A11 *= 3; /* :420-425, single channel only */
+        A12 *= 3;
+        A22 *= 3;
+        B1 *= 3;
+        B2 *= 3;
+      } else { /* RGB branch: one robust weight over the three channels, no final x3 */
+        float t[6], nn[6], psi;
+        if (hd) {
+          for (ch = 0; ch < 3; ++ch) {
+            t[ch] = Iz[ch][k] + Ix[ch][k] * du[k] + Iy[ch][k] * dv[k];
+            nn[ch] = Ix[ch][k] * Ix[ch][k] + Iy[ch][k] * Iy[ch][k] + dnorm;
+          }
+          psi = mask[k] * hd / sqrtf(t[0] * t[0] / nn[0] + t[1] * t[1] / nn[1] + t[2] * t[2] / nn[2] + eps);
+          for (ch = 0; ch < 3; ++ch) {
+            const float tc = psi / nn[ch]; /* tmp3 = tmp/n3; tmp2 = tmp/n2; tmp /= n1 */
+            A11 += tc * Ix[ch][k] * Ix[ch][k];
+            A12 += tc * Ix[ch][k] * Iy[ch][k];
+            A22 += tc * Iy[ch][k] * Iy[ch][k];
+            B1 -= tc * Iz[ch][k] * Ix[ch][k];
+            B2 -= tc * Iz[ch][k] * Iy[ch][k];
+          }
+        }
+        for (ch = 0; ch < 3; ++ch) {
+          nn[2 * ch] = Ixx[ch][k] * Ixx[ch][k] + Ixy[ch][k] * Ixy[ch][k] + dnorm;
+          nn[2 * ch + 1] = Iyy[ch][k] * Iyy[ch][k] + Ixy[ch][k] * Ixy[ch][k] + dnorm;
+          t[2 * ch] = Ixz[ch][k] + Ixx[ch][k] * du[k] + Ixy[ch][k] * dv[k];
+          t[2 * ch + 1] = Iyz[ch][k] + Ixy[ch][k] * du[k] + Iyy[ch][k] * dv[k];
+        }
+        psi = mask[k] * hg / sqrtf(t[0] * t[0] / nn[0] + t[1] * t[1] / nn[1] + t[2] * t[2] / nn[2] + t[3] * t[3] / nn[3] +
+                                   t[4] * t[4] / nn[4] + t[5] * t[5] / nn[5] + eps);
+        for (ch = 0; ch < 3; ++ch) {
+          const float ta = psi / nn[2 * ch], tb = psi / nn[2 * ch + 1];
+          A11 += ta * Ixx[ch][k] * Ixx[ch][k] + tb * Ixy[ch][k] * Ixy[ch][k];
+          A12 += ta * Ixx[ch][k] * Ixy[ch][k] + tb * Ixy[ch][k] * Iyy[ch][k];
+          A22 += tb * Iyy[ch][k] * Iyy[ch][k] + ta * Ixy[ch][k] * Ixy[ch][k];
+          B1 -= ta * Ixx[ch][k] * Ixz[ch][k] + tb * Ixy[ch][k] * Iyz[ch][k];
+          B2 -= tb * Iyy[ch][k] * Iyz[ch][k] + ta * Ixy[ch][k] * Ixz[ch][k];
+        }
       }
-      n1 = Ixx[k] * Ixx[k] + Ixy[k] * Ixy[k] + dnorm;
-      n2 = Iyy[k] * Iyy[k] + Ixy[k] * Ixy[k] + dnorm;
-      tmp = Ixz[k] + Ixx[k] * du[k] + Ixy[k] * dv[k];
-      tmp2 = Iyz[k] + Ixy[k] * du[k] + Iyy[k] * dv[k];
-      tmp = mask[k] * hg / sqrtf(3 * tmp * tmp / n1 + 3 * tmp2 * tmp2 / n2 + eps);
-      tmp2 = tmp / n2;
-      tmp /= n1;
-      A11 += tmp * Ixx[k] * Ixx[k] + tmp2 * Ixy[k] * Ixy[k];
-      A12 += tmp * Ixx[k] * Ixy[k] + tmp2 * Ixy[k] * Iyy[k];
-      A22 += tmp2 * Iyy[k] * Iyy[k] + tmp * Ixy[k] * Ixy[k];
-      B1 -= tmp * Ixx[k] * Ixz[k] + tmp2 * Ixy[k] * Iyz[k];
-      B2 -= tmp2 * Iyy[k] * Iyz[k] + tmp * Ixy[k] * Ixz[k];
-      a11[k] = A11 * 3;
-      a12[k] = A12 * 3;
-      a22[k] = A22 * 3;
-      b1[k] = B1 * 3;
-      b2[k] = B2 * 3;
+      a11[k] = A11;
+      a12[k] = A12;
+      a22[k] = A22;
+      b1[k] = B1;
+      b2[k] = B2;
     }
     /* sub_laplacian x2, opticalflow_aux.c:172-199 (horizontal pass, then vertical pass) */
     for (k = 0; k < 2; ++k) {
@@ -743,13 +834,13 @@ ORACLE_API int oracle_engine(const float* const* im_ao, const float* const* im_a
                              const float* const* im_ao_dy, const float* const* im_bo,
                              const float* const* im_bo_dx, const float* const* im_bo_dy, int imgpadding,
                              float* outflow, const float* initflow, int width, int height,
-                             const dis_params* q, float** tap_pflow, float** tap_dense) {
+                             const dis_params* q, float** tap_pflow, float** tap_dense, int noc) {
   opt_t o;
   const int noscales = q->lv_f - q->lv_l + 1;
   float** flow_fw = (float**)calloc(noscales, sizeof(float*));
   float** flow_bw = (float**)calloc(noscales, sizeof(float*));
   int sl;
-  make_opt(q, &o);
+  make_opt(q, noc, &o);
   for (sl = q->lv_f; sl >= q->lv_l; --sl) {
     const int ii = sl - q->lv_l;
     lvl_t c;
@@ -785,8 +876,8 @@ ORACLE_API int oracle_engine(const float* const* im_ao, const float* const* im_a
       memcpy(tap_dense[sl], out, sizeof(float) * 2 * c.w * c.h);
     }
     if (q->usetvref) {
-      oracle_varref(im_ao[sl], im_bo[sl], &c, q, out);
-      if (q->usefbcon && sl > q->lv_l) oracle_varref(im_bo[sl], im_ao[sl], &c, q, flow_bw[ii]);
+      oracle_varref(im_ao[sl], im_bo[sl], &c, q, noc, out);
+      if (q->usefbcon && sl > q->lv_l) oracle_varref(im_bo[sl], im_ao[sl], &c, q, noc, flow_bw[ii]);
     }
     free(pflow);
     free(pweight);
@@ -848,20 +939,20 @@ ORACLE_API void oracle_finish(const float* flow_l, int wl, int hl, int lv_l, int
 
 /* Whole run_dense data path on decoded grey images (kroeger/run_dense.cpp:298-414).
  * flow_out: w*h*2 (full resolution); level_out (optional): raw engine output at level lv_l. */
-ORACLE_API int oracle_run_u8(const uint8_t* a, const uint8_t* b, int w, int h, int pitch,
-                             const dis_params* q, float* flow_out, float* level_out) {
+ORACLE_API int oracle_run_u8c(const uint8_t* a, const uint8_t* b, int w, int h, int pitch, int noc,
+                              const dis_params* q, float* flow_out, float* level_out) {
   const int nl = q->lv_f + 1;
   float** P[6];
   int wp, hp, left, top, k, l;
   float* lvl;
   oracle_padded_size(w, h, q->lv_f, &wp, &hp, &left, &top);
   for (k = 0; k < 6; ++k) P[k] = (float**)calloc(nl, sizeof(float*));
-  oracle_build_pyramid(a, w, h, pitch, q->lv_f, q->patchsz, P[0], P[1], P[2]);
-  oracle_build_pyramid(b, w, h, pitch, q->lv_f, q->patchsz, P[3], P[4], P[5]);
+  oracle_build_pyramid_c(a, w, h, pitch, noc, q->lv_f, q->patchsz, P[0], P[1], P[2]);
+  oracle_build_pyramid_c(b, w, h, pitch, noc, q->lv_f, q->patchsz, P[3], P[4], P[5]);
   lvl = (float*)malloc(sizeof(float) * 2 * (wp >> q->lv_l) * (hp >> q->lv_l));
   oracle_engine((const float* const*)P[0], (const float* const*)P[1], (const float* const*)P[2],
                 (const float* const*)P[3], (const float* const*)P[4], (const float* const*)P[5],
-                q->patchsz, lvl, NULL, wp, hp, q, NULL, NULL);
+                q->patchsz, lvl, NULL, wp, hp, q, NULL, NULL, noc);
   if (level_out) memcpy(level_out, lvl, sizeof(float) * 2 * (wp >> q->lv_l) * (hp >> q->lv_l));
   if (flow_out) oracle_finish(lvl, wp >> q->lv_l, hp >> q->lv_l, q->lv_l, left, top, w, h, flow_out);
   free(lvl);
@@ -870,4 +961,9 @@ ORACLE_API int oracle_run_u8(const uint8_t* a, const uint8_t* b, int w, int h, i
     free(P[k]);
   }
   return 0;
+}
+
+ORACLE_API int oracle_run_u8(const uint8_t* a, const uint8_t* b, int w, int h, int pitch,
+                             const dis_params* q, float* flow_out, float* level_out) {
+  return oracle_run_u8c(a, b, w, h, pitch, 1, q, flow_out, level_out);
 }

@@ -96,7 +96,7 @@ def _ptrs(arrs):
     return a
 
 
-def run_engine(pyr_a, pyr_b, w_pad, h_pad, params, initflow=None, taps=False):
+def run_engine(pyr_a, pyr_b, w_pad, h_pad, params, initflow=None, taps=False, noc=1):
     """E1 restatement (= OFC::OFClass ctor). pyr_* = (I, Ix, Iy) lists. Returns flow at level lv_l;
     with taps=True also ({level: patch_flow}, {level: dense_flow_before_refinement})."""
     L = lib()
@@ -108,7 +108,7 @@ def run_engine(pyr_a, pyr_b, w_pad, h_pad, params, initflow=None, taps=False):
     ptrs = [_ptrs(x) for x in (*pyr_a, *pyr_b)]
     L.oracle_engine(*ptrs, q.patchsz, flow.ctypes.data_as(_fp),
                     initflow.ctypes.data_as(_fp) if initflow is not None else None, w_pad, h_pad,
-                    ctypes.byref(q), tp, td)
+                    ctypes.byref(q), tp, td, noc)
     if not taps:
         return flow
     steps = max(1, int(np.floor(q.patchsz * (1 - q.poverl))))
@@ -125,17 +125,18 @@ def run_engine(pyr_a, pyr_b, w_pad, h_pad, params, initflow=None, taps=False):
 
 def run_u8(a_u8, b_u8, params, want_level=False):
     """Whole run_dense data path restated (P1 + E1 + O1). Returns full-res flow (h, w, 2)
-    [and the raw level-lv_l engine output]."""
+    [and the raw level-lv_l engine output].  Grey (h, w) or interleaved BGR (h, w, 3) u8 input."""
     L = lib()
     a_u8 = np.ascontiguousarray(a_u8, np.uint8)
     b_u8 = np.ascontiguousarray(b_u8, np.uint8)
-    h, w = a_u8.shape
+    h, w = a_u8.shape[:2]
+    noc = 1 if a_u8.ndim == 2 else a_u8.shape[2]
     q = DisParams.from_dict(params)
     wp, hp, _, _ = padded_size(w, h, q.lv_f)
     flow = np.zeros((h, w, 2), np.float32)
     lvl = np.zeros((hp >> q.lv_l, wp >> q.lv_l, 2), np.float32)
-    L.oracle_run_u8(a_u8.ctypes.data_as(ctypes.c_void_p), b_u8.ctypes.data_as(ctypes.c_void_p), w, h,
-                    a_u8.strides[0], ctypes.byref(q), flow.ctypes.data_as(_fp), lvl.ctypes.data_as(_fp))
+    L.oracle_run_u8c(a_u8.ctypes.data_as(ctypes.c_void_p), b_u8.ctypes.data_as(ctypes.c_void_p), w, h,
+                     a_u8.strides[0], noc, ctypes.byref(q), flow.ctypes.data_as(_fp), lvl.ctypes.data_as(_fp))
     return (flow, lvl) if want_level else flow
 
 
