@@ -100,6 +100,7 @@ def lib():
         L.dis_padded_size.argtypes = [ip, ip, ip] + [ctypes.POINTER(ip)] * 4
         L.dis_auto_first_scale.argtypes = [ip, ip, ip]
         L.dis_create.argtypes = [pp, ip, ip, ip, ctypes.POINTER(vp)]
+        L.dis_create_c.argtypes = [pp, ip, ip, ip, ip, ctypes.POINTER(vp)]
         L.dis_destroy.argtypes = [vp]
         L.dis_set_params.argtypes = [vp, pp]
         L.dis_run_pyramids.argtypes = [vp] + [fpp] * 6 + [ip, ip, ip, fp, fp]
@@ -164,11 +165,14 @@ _PINNED = {}
 class Engine:
     """One engine instance = one dis_handle (stream, workspace, CUDA graph)."""
 
-    def __init__(self, params, max_w, max_h, device=0):
+    def __init__(self, params, max_w, max_h, device=0, channels=1):
+        """channels=1: grey (the reference's run_OF_INT build); channels=3: interleaved BGR
+        (run_OF_RGB, SELECTCHANNEL=3)."""
         self._h = ctypes.c_void_p()
         self.params = params if isinstance(params, Params) else Params.from_dict(params)
-        _check(lib().dis_create(ctypes.byref(self.params), int(max_w), int(max_h), int(device),
-                                ctypes.byref(self._h)), None)
+        self.channels = int(channels)
+        _check(lib().dis_create_c(ctypes.byref(self.params), self.channels, int(max_w), int(max_h), int(device),
+                                  ctypes.byref(self._h)), None)
         self._keep = None
 
     def close(self):
@@ -194,16 +198,24 @@ class Engine:
 
     # ---- whole run_dense data path ----------------------------------------------------------
     def run_u8(self, a, b, out=None):
-        """Grey u8 frames (h, w) -> full-resolution flow (h, w, 2) float32. Synchronous."""
+        """Grey u8 frames (h, w) [channels=3: BGR (h, w, 3)] -> full-resolution flow (h, w, 2) float32.
+        Synchronous."""
         self.submit_u8(a, b, out)
         return self.wait()
 
     def submit_u8(self, a, b, out=None):
-        a = np.ascontiguousarray(a, np.uint8) if not (a.dtype == np.uint8 and a.strides[1] == 1) else a
-        b = np.ascontiguousarray(b, np.uint8) if not (b.dtype == np.uint8 and b.strides[1] == 1) else b
-        if a.ndim != 2 or a.shape != b.shape or a.strides[0] != b.strides[0]:
-            raise ValueError("need two grey u8 images of identical shape and pitch")
-        h, w = a.shape
+        def rows_ok(x):  # u8, pixels (and channels) contiguous within a row
+            if x.dtype != np.uint8 or x.strides[-1] != 1:
+                return False
+            return x.ndim == 2 or x.strides[1] == x.shape[2]
+        a = a if rows_ok(a) else np.ascontiguousarray(a, np.uint8)
+        b = b if rows_ok(b) else np.ascontiguousarray(b, np.uint8)
+        want = (3, 3) if self.channels == 3 else (2, None)
+        if a.ndim != want[0] or (a.ndim == 3 and a.shape[2] != want[1]) or a.shape != b.shape or \
+                a.strides[0] != b.strides[0]:
+            raise ValueError("need two %s u8 images of identical shape and pitch" %
+                             ("BGR (h, w, 3)" if self.channels == 3 else "grey (h, w)"))
+        h, w = a.shape[:2]
         if out is None:
             out = np.empty((h, w, 2), np.float32)
         self._keep = (a, b, out)
@@ -292,8 +304,8 @@ def OFClass(im_ao, im_ao_dx, im_ao_dy, im_bo, im_bo_dx, im_bo_dy, imgpadding, ou
             device=0):
     """Same positional arguments as ``OFC::OFClass::OFClass`` (kroeger/oflow.h:84-111); like the
     reference, all work happens in this call and the result is written into ``outflow``."""
-    if noc != 1:
-        raise DisError(2, "only noc=1 (grey, SELECTCHANNEL=1) is supported")
+    if noc not in (1, 3):
+        raise DisError(2, "noc must be 1 (grey, SELECTCHANNEL=1) or 3 (RGB, SELECTCHANNEL=3)")
     if imgpadding != p_samp_s:
         raise DisError(2, "imgpadding must equal the patch size (kroeger/run_dense.cpp:393)")
     p = Params.from_dict(dict(lv_f=sc_f, lv_l=sc_l, maxiter=max_iter, miniter=min_iter, mindprate=dp_thresh,
@@ -301,7 +313,7 @@ def OFClass(im_ao, im_ao_dx, im_ao_dy, im_bo, im_bo_dx, im_bo_dy, imgpadding, ou
                               usefbcon=int(usefbcon), patnorm=patnorm, costfct=costfct, usetvref=int(usetvref),
                               tv_alpha=tv_alpha, tv_gamma=tv_gamma, tv_delta=tv_delta, tv_innerit=tv_innerit,
                               tv_solverit=tv_solverit, tv_sor=tv_sor, verbosity=verbosity))
-    with Engine(p, width, height, device) as e:
+    with Engine(p, width, height, device, channels=noc) as e:
         fl = e.run_pyramids((im_ao, im_ao_dx, im_ao_dy), (im_bo, im_bo_dx, im_bo_dy), width, height, initflow)
     np.asarray(outflow).reshape(fl.shape)[...] = fl
     return outflow

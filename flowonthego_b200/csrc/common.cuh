@@ -20,11 +20,12 @@ struct LevelGeom {
   float lb, ubw, ubh;  // valid region for patch centres (oflow.cpp:147-149)
   int nopw, noph, offw, offh, nop;  // patch grid
   int fpitch;      // pitch (in pixels) of per-level planar/float2 work images (= w)
+  int noc;         // channels of the padded images: 1 grey, 3 interleaved BGR (SELECTCHANNEL=3); pitch counts floats
 };
 
 // Parameters derived in OFClass::OFClass (kroeger/oflow.cpp:75-108)
 struct OptParams {
-  int p, novals, steps, max_iter, min_iter, patnorm, costfct;
+  int p, novals, steps, max_iter, min_iter, patnorm, costfct, noc;
   float outlierthresh, dp_thresh, dr_thresh, res_thresh;
 };
 

@@ -22,6 +22,21 @@ namespace {
 
 __device__ __forceinline__ float absw_of(float w) { return 1.0f / (2.0f < w ? w : 2.0f); }
 
+// Pixel weight of patch element (lx,ly) (kroeger/patchgrid.cpp:253-260, 330-337).  Grey: 1/max(2,w).  RGB:
+// 1/(max(2,w0)+max(2,w1)+max(2,w2)) -- read through the reference's own pointer walk, which advances by 3 for
+// pixels that pass the bounds test and by 1 for skipped ones (so the channels of border patches are misaligned;
+// reproduced as is): offset = (#pixels before) + 2*(#accepted pixels before), the accepted pixels forming the
+// rectangle [xlo,xhi] x [ylo,yhi] in patch coordinates.
+__device__ __forceinline__ float patch_absw(const float* pw, int P, int noc, int lx, int ly, int xlo, int xhi, int ylo) {
+  if (noc == 1) return absw_of(__ldg(pw + ly * P + lx));
+  const int off = (ly * P + lx) + 2 * ((ly - ylo) * (xhi - xlo + 1) + (lx - xlo));
+  const float w0 = __ldg(pw + off), w1 = __ldg(pw + off + 1), w2 = __ldg(pw + off + 2);
+  float a = (2.0f < w0 ? w0 : 2.0f);
+  a += (2.0f < w1 ? w1 : 2.0f);
+  a += (2.0f < w2 ? w2 : 2.0f);
+  return 1.0f / a;
+}
+
 // Per-patch integer anchor ceil(pt_iter + 1e-5) (double arithmetic, patchgrid.cpp:304-305), bilinear
 // weights (:310-315) and the level-wide maximum anchor displacement.
 __global__ void __launch_bounds__(256) k_bw_anchors(const LevelGeom g, const OptParams o, const float2* __restrict__ pflow,
@@ -85,19 +100,22 @@ __global__ void __launch_bounds__(256) k_densify(const DensifyArgs a) {
           fv += fl[u * C + v].y * aw;
         }
   };
-  if (a.cover <= 2) {
+  const int noc = a.o.noc;
+  if (noc == 1 && a.cover <= 2) {
     gather_fixed(std::integral_constant<int, 2>{});
-  } else if (a.cover <= 4) {
+  } else if (noc == 1 && a.cover <= 4) {
     gather_fixed(std::integral_constant<int, 4>{});
   } else {
     for (int gx = gx0; gx <= gx1; ++gx) {
-      const int lx = x - (gx * steps + a.g.offw) + half;
+      const int pcx = gx * steps + a.g.offw;
+      const int lx = x - pcx + half;
+      const int xlo = max(0, half - pcx), xhi = min(P - 1, a.g.w - 1 - pcx + half);
       for (int gy = gy0; gy <= gy1; ++gy) {
         const int ip = gx * a.g.noph + gy;
-        const int ly = y - (gy * steps + a.g.offh) + half;
-        const float w = __ldg(a.pweight + (size_t)ip * N + ly * P + lx);
+        const int pcy = gy * steps + a.g.offh;
+        const int ly = y - pcy + half;
         const float2 f = __ldg(a.pflow + ip);
-        const float aw = absw_of(w);
+        const float aw = patch_absw(a.pweight + (size_t)ip * N, P, noc, lx, ly, xlo, xhi, max(0, half - pcy));
         we += aw;
         fu += f.x * aw;
         fv += f.y * aw;
@@ -124,10 +142,12 @@ __global__ void __launch_bounds__(256) k_densify(const DensifyArgs a) {
         const float4 wb = __ldg(a.wbil + ip);
         const float* pw = a.pweight_bw + (size_t)ip * N;
         // source element (ex,ey) of the patch sits at target (XT,YT) and feeds this pixel with weight wk
+        // accepted source pixels of this patch (xt,yt in [1,w-2] x [1,h-2]) as a rectangle in patch coordinates
+        const int bxlo = max(0, 1 - an.x - lb), bxhi = min(P - 1, w - 2 - an.x - lb), bylo = max(0, 1 - an.y - lb);
         auto contrib = [&](int ex, int ey, int XT, int YT, float wk) {
           if (ex < lb || ex > ub || ey < lb || ey > ub) return;
           if (!(XT >= 1 && YT >= 1 && XT < (w - 1) && YT < (h - 1))) return;
-          const float aw = absw_of(__ldg(pw + (ey - lb) * P + (ex - lb)));
+          const float aw = patch_absw(pw, P, a.o.noc, ex - lb, ey - lb, bxlo, bxhi, bylo);
           const float f0 = f.x * aw, f1 = f.y * aw;
           we += wk * aw;
           fu -= wk * f0;

@@ -82,6 +82,7 @@ struct dis_handle {
   int device = 0;
   cudaStream_t stream = nullptr;
   dis_params P{};
+  int noc = 1;  // image channels: 1 grey (SELECTCHANNEL=1), 3 interleaved BGR (SELECTCHANNEL=3)
   OptParams opt{};
   int max_w = 0, max_h = 0;
   std::string err;
@@ -144,7 +145,8 @@ int fail(dis_handle* h, int code, const char* fmt, ...) {
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // kroeger/oflow.cpp:75-108
-void derive_opt(const dis_params& q, OptParams* o) {
+void derive_opt(const dis_params& q, int noc, OptParams* o) {
+  o->noc = noc;
   o->p = q.patchsz;
   o->outlierthresh = (float)o->p / 2;
   o->max_iter = q.maxiter;
@@ -153,13 +155,14 @@ void derive_opt(const dis_params& q, OptParams* o) {
   o->dr_thresh = q.mindrrate;
   o->res_thresh = q.minimgerr;
   o->steps = std::max(1, (int)floor(o->p * (1 - q.poverl)));
-  o->novals = o->p * o->p;
+  o->novals = noc * o->p * o->p;  // oflow.cpp:92
   o->patnorm = q.patnorm;
   o->costfct = q.costfct;
 }
 
 // kroeger/oflow.cpp:138-160 (camparam) and kroeger/patchgrid.cpp:42-49 (grid geometry)
 void derive_level(const OptParams& o, int width, int height, int pad, int sl, LevelGeom* g) {
+  g->noc = o.noc;
   const float sc_fct = (float)pow(2, -sl);
   g->lv = sl;
   g->h = (int)(height * sc_fct);
@@ -167,7 +170,7 @@ void derive_level(const OptParams& o, int width, int height, int pad, int sl, Le
   g->pad = pad;
   g->tw = g->w + 2 * pad;
   g->th = g->h + 2 * pad;
-  g->pitch = (int)align_up((size_t)g->tw, 32);
+  g->pitch = (int)align_up((size_t)g->tw * o.noc, 32);
   g->lb = -(float)o.p / 2;
   g->ubw = (float)(g->w + o.p / 2 - 2);
   g->ubh = (float)(g->h + o.p / 2 - 2);
@@ -198,8 +201,8 @@ size_t carve(dis_handle* h, int w, int h_img, char* base, bool assign) {
   dis_padded_size(w, h_img, q.lv_f, &wp, &hp, &left, &top);
   Carver c{base};
   std::vector<LevelBufs> lv(q.lv_f + 1);
-  uint8_t* d_a = c.take<uint8_t>((size_t)w * h_img);
-  uint8_t* d_b = c.take<uint8_t>((size_t)w * h_img);
+  uint8_t* d_a = c.take<uint8_t>((size_t)w * h_img * h->noc);
+  uint8_t* d_b = c.take<uint8_t>((size_t)w * h_img * h->noc);
   for (int l = 0; l <= q.lv_f; ++l) {
     LevelBufs& L = lv[l];
     derive_level(h->opt, wp, hp, q.patchsz, l, &L.g);
@@ -232,8 +235,9 @@ size_t carve(dis_handle* h, int w, int h_img, char* base, bool assign) {
   VarRefBuffers vb{};
   if (q.usetvref) {
     const size_t n = (size_t)gf.w * gf.h;
-    float** planes[] = {&vb.avg, &vb.Iz, &vb.mask, &vb.Ix, &vb.Iy, &vb.Ixx, &vb.Ixy, &vb.Iyy, &vb.Ixz, &vb.Iyz};
-    for (float** p : planes) *p = c.take<float>(n);
+    float** planes[] = {&vb.avg, &vb.Iz, &vb.Ix, &vb.Iy, &vb.Ixx, &vb.Ixy, &vb.Iyy, &vb.Ixz, &vb.Iyz};
+    for (float** p : planes) *p = c.take<float>(n * h->noc);  // one plane per colour channel
+    vb.mask = c.take<float>(n);
     size_t n_coef4, n_du4, n_prog;
     varref_sizes(gf.w, gf.h, std::max(1, q.tv_solverit), &n_coef4, &n_du4, &n_prog);
     vb.coefA = c.take<float4>(n_coef4);
@@ -315,8 +319,8 @@ void tap_image(dis_handle* h, int tap, int level, const float* d, const LevelGeo
   if ((int)h->tapdata.size() <= tap) h->tapdata.resize(tap + 1);
   if ((int)h->tapdata[tap].size() <= level) h->tapdata[tap].resize(level + 1);
   auto& v = h->tapdata[tap][level].data;
-  v.resize((size_t)g.tw * g.th);
-  cudaMemcpy2DAsync(v.data(), sizeof(float) * g.tw, d, sizeof(float) * g.pitch, sizeof(float) * g.tw, g.th,
+  v.resize((size_t)g.tw * g.th * g.noc);
+  cudaMemcpy2DAsync(v.data(), sizeof(float) * g.tw * g.noc, d, sizeof(float) * g.pitch, sizeof(float) * g.tw * g.noc, g.th,
                     cudaMemcpyDeviceToHost, h->stream);
   cudaStreamSynchronize(h->stream);
 }
@@ -635,8 +639,13 @@ int dis_padded_size(int w, int h, int lv_f, int* w_pad, int* h_pad, int* left, i
 const char* dis_last_error(const dis_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 int dis_create(const dis_params* params, int max_w, int max_h, int device, dis_handle** out) {
+  return dis_create_c(params, 1, max_w, max_h, device, out);
+}
+
+int dis_create_c(const dis_params* params, int channels, int max_w, int max_h, int device, dis_handle** out) {
   if (!out) return fail(nullptr, DIS_ERR_INVALID_ARG, "out is null");
   *out = nullptr;
+  if (channels != 1 && channels != 3) return fail(nullptr, DIS_ERR_UNSUPPORTED, "channels must be 1 (grey) or 3 (BGR)");
   char why[128];
   int rc = dis_params_validate(params, why, sizeof why);
   if (rc != DIS_OK) return fail(nullptr, rc, "invalid parameters: %s", why);
@@ -656,7 +665,8 @@ int dis_create(const dis_params* params, int max_w, int max_h, int device, dis_h
   dis_handle* h = new dis_handle;
   h->device = device;
   h->P = *params;
-  derive_opt(h->P, &h->opt);
+  h->noc = channels;
+  derive_opt(h->P, h->noc, &h->opt);
   h->max_w = max_w;
   h->max_h = max_h;
   if ((e = cudaSetDevice(device)) != cudaSuccess ||
@@ -696,7 +706,7 @@ int dis_set_params(dis_handle* h, const dis_params* params) {
   CU(h, cudaSetDevice(h->device));
   CU(h, cudaStreamSynchronize(h->stream));
   h->P = *params;
-  derive_opt(h->P, &h->opt);
+  derive_opt(h->P, h->noc, &h->opt);
   const int w = h->w_org, hh = h->h_org;
   h->lv.clear();
   h->w_org = h->h_org = 0;
@@ -762,7 +772,7 @@ int dis_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? DIS_OK 
 
 int dis_submit_u8_device(dis_handle* h, const uint8_t* d_a, const uint8_t* d_b, int w, int h_img, int pitch,
                          float* d_flow) {
-  if (!h || !d_a || !d_b || !d_flow || pitch < w) return h ? fail(h, DIS_ERR_INVALID_ARG, "bad argument") : DIS_ERR_INVALID_ARG;
+  if (!h || !d_a || !d_b || !d_flow || pitch < w * h->noc) return h ? fail(h, DIS_ERR_INVALID_ARG, "bad argument") : DIS_ERR_INVALID_ARG;
   CU(h, cudaSetDevice(h->device));
   int rc = plan(h, w, h_img);
   if (rc != DIS_OK) return rc;
@@ -773,7 +783,7 @@ int dis_submit_u8_device(dis_handle* h, const uint8_t* d_a, const uint8_t* d_b, 
 }
 
 int dis_submit_u8(dis_handle* h, const uint8_t* a, const uint8_t* b, int w, int h_img, int pitch, float* flow_out) {
-  if (!h || !a || !b || !flow_out || pitch < w) return h ? fail(h, DIS_ERR_INVALID_ARG, "bad argument") : DIS_ERR_INVALID_ARG;
+  if (!h || !a || !b || !flow_out || pitch < w * h->noc) return h ? fail(h, DIS_ERR_INVALID_ARG, "bad argument") : DIS_ERR_INVALID_ARG;
   CU(h, cudaSetDevice(h->device));
   int rc = plan(h, w, h_img);
   if (rc != DIS_OK) return rc;
@@ -783,10 +793,11 @@ int dis_submit_u8(dis_handle* h, const uint8_t* a, const uint8_t* b, int w, int 
   CU(h, cudaEventCreate(&h->ev[2]));
   CU(h, cudaEventCreate(&h->ev[3]));
   CU(h, cudaEventRecord(h->ev[0], h->stream));
-  CU(h, cudaMemcpy2DAsync(h->d_a, w, a, pitch, w, h_img, cudaMemcpyHostToDevice, h->stream));
-  CU(h, cudaMemcpy2DAsync(h->d_b, w, b, pitch, w, h_img, cudaMemcpyHostToDevice, h->stream));
+  const size_t rowb = (size_t)w * h->noc;
+  CU(h, cudaMemcpy2DAsync(h->d_a, rowb, a, pitch, rowb, h_img, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpy2DAsync(h->d_b, rowb, b, pitch, rowb, h_img, cudaMemcpyHostToDevice, h->stream));
   CU(h, cudaEventRecord(h->ev[1], h->stream));
-  rc = enqueue_run_device(h, h->d_a, h->d_b, w, h->d_out);
+  rc = enqueue_run_device(h, h->d_a, h->d_b, (int)rowb, h->d_out);
   if (rc != DIS_OK) return rc;
   CU(h, cudaEventRecord(h->ev[2], h->stream));
   CU(h, cudaMemcpyAsync(flow_out, h->d_out, sizeof(float2) * (size_t)w * h_img, cudaMemcpyDeviceToHost, h->stream));
@@ -864,8 +875,8 @@ int dis_run_pyramids(dis_handle* h, const float* const* im_ao, const float* cons
     for (int k = 0; k < 6; ++k) {
       if (!dst[k]) continue;
       if (!src[k]) return fail(h, DIS_ERR_INVALID_ARG, "pyramid %d level %d is null", k, l);
-      CU(h, cudaMemcpy2DAsync(dst[k], sizeof(float) * L.g.pitch, src[k], sizeof(float) * L.g.tw,
-                              sizeof(float) * L.g.tw, L.g.th, cudaMemcpyHostToDevice, h->stream));
+      CU(h, cudaMemcpy2DAsync(dst[k], sizeof(float) * L.g.pitch, src[k], sizeof(float) * L.g.tw * L.g.noc,
+                              sizeof(float) * L.g.tw * L.g.noc, L.g.th, cudaMemcpyHostToDevice, h->stream));
     }
   }
   float2* d_init = nullptr;

@@ -46,16 +46,24 @@ struct Win {
   static constexpr int SIZE = W * W;
 };
 
-template <int P, bool L2>
+//
+// NC = 3 (the reference's SELECTCHANNEL=3 build): a patch row is 3P interleaved floats and the same
+// chain rule applies to the 3P^2 values (patch.cpp:392-396); the target taps are then read straight
+// from global memory (L1/L2) instead of a staged window, and for p > 8 the template and gradients are
+// re-read per iteration instead of being held in registers.
+template <int P, bool L2, int NC>
 __global__ void __launch_bounds__(128) k_patch_search(const PatchSearchArgs a) {
-  constexpr int N = P * P;
+  constexpr int N = P * P * NC;
+  constexpr int PW = P * NC;            // floats per patch row
   constexpr int NI = N / 8;             // chain length
   constexpr bool EX = (N % 8) == 4;     // trailing packet present
   constexpr int NE = NI + (EX ? 1 : 0);
   constexpr int LB = -P / 2;
-  constexpr int M = P / gcd_ce(8, P);   // period of the (row, col) pattern of elements 8i + c
-  constexpr int ROWS = 8 * M / P;       // rows advanced per period
+  constexpr int M = PW / gcd_ce(8, PW); // period of the (row, col) pattern of elements 8i + c
+  constexpr int ROWS = 8 * M / PW;      // rows advanced per period
   constexpr int WIN = Win<P>::W;
+  constexpr bool SMEM = NC == 1;        // target window staged in shared memory
+  constexpr bool REG = NE <= 32;        // template + gradients held in registers
   extern __shared__ float smem_win[];
 
   const int c = threadIdx.x & 7;
@@ -73,46 +81,62 @@ __global__ void __launch_bounds__(128) k_patch_search(const PatchSearchArgs a) {
 #pragma unroll
   for (int m = 0; m < M; ++m) {
     const int e = 8 * m + c;
-    prow[m] = e / P;
-    pcol[m] = e % P;
+    prow[m] = e / PW;
+    pcol[m] = e % PW;
   }
   const int te = 8 * NI + (c & 3);  // tail element (EX only)
-  const int trow = te / P, tcol = te % P;
+  const int trow = te / PW, tcol = te % PW;
 
   // ---- InitializePatch: template and gradients at the integer patch centre (patch.cpp:287-332)
-  float T[NE], GX[NE], GY[NE];
-  {
-    const size_t base = (size_t)(cy + pad + LB) * pitch + (cx + pad + LB);
+  constexpr int NR = REG ? NE : 1;
+  float T[NR], GX[NR], GY[NR];
+  const size_t base = (size_t)(cy + pad + LB) * pitch + (cx + pad + LB) * NC;
+  // offset of chain element i from the patch origin (padded image coordinates)
+  auto eoff = [&](int i) -> int {
+    return (i < NI) ? (prow[i % M] + (i / M) * ROWS) * pitch + pcol[i % M] : trow * pitch + tcol;
+  };
+  float tmean = 0.0f;  // x - 0.0f == x exactly: no branch needed where it is subtracted
+  if (REG) {
 #pragma unroll
     for (int i = 0; i < NE; ++i) {
-      const int m = i % M, k = i / M;
-      const size_t o = (i < NI) ? base + (size_t)(prow[m] + k * ROWS) * pitch + pcol[m] : base + (size_t)trow * pitch + tcol;
+      const size_t o = base + eoff(i);
       T[i] = __ldg(a.I0 + o);
       GX[i] = __ldg(a.I0x + o);
       GY[i] = __ldg(a.I0y + o);
     }
   }
   if (a.o.patnorm > 0) {
-    float ch = T[0];
+    float ch = 0.0f, ex = 0.0f;
 #pragma unroll
-    for (int i = 1; i < NI; ++i) ch = ch + T[i];
-    const float m = octet_reduce<EX>(ch, EX ? T[NE - 1] : 0.0f) / (float)N;
+    for (int i = 0; i < NE; ++i) {
+      const float t = REG ? T[i] : __ldg(a.I0 + base + eoff(i));
+      if (i == 0) ch = t; else if (i < NI) ch = ch + t; else ex = t;
+    }
+    tmean = octet_reduce<EX>(ch, ex) / (float)N;
+    if (REG) {
 #pragma unroll
-    for (int i = 0; i < NE; ++i) T[i] = T[i] - m;
+      for (int i = 0; i < NE; ++i) T[i] = T[i] - tmean;
+    }
   }
   // ---- ComputeHessian (patch.cpp:71-88)
   float H00, H01, H11;
   {
-    float c0 = GX[0] * GX[0], c1 = GX[0] * GY[0], c2 = GY[0] * GY[0];
+    float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, e0 = 0.0f, e1 = 0.0f, e2 = 0.0f;
 #pragma unroll
-    for (int i = 1; i < NI; ++i) {
-      c0 = c0 + GX[i] * GX[i];
-      c1 = c1 + GX[i] * GY[i];
-      c2 = c2 + GY[i] * GY[i];
+    for (int i = 0; i < NE; ++i) {
+      const float gx_ = REG ? GX[i] : __ldg(a.I0x + base + eoff(i));
+      const float gy_ = REG ? GY[i] : __ldg(a.I0y + base + eoff(i));
+      if (i == 0) {
+        c0 = gx_ * gx_; c1 = gx_ * gy_; c2 = gy_ * gy_;
+      } else if (i < NI) {
+        c0 = c0 + gx_ * gx_; c1 = c1 + gx_ * gy_; c2 = c2 + gy_ * gy_;
+      } else {
+        e0 = gx_ * gx_; e1 = gx_ * gy_; e2 = gy_ * gy_;
+      }
     }
-    H00 = octet_reduce<EX>(c0, EX ? GX[NE - 1] * GX[NE - 1] : 0.0f);
-    H01 = octet_reduce<EX>(c1, EX ? GX[NE - 1] * GY[NE - 1] : 0.0f);
-    H11 = octet_reduce<EX>(c2, EX ? GY[NE - 1] * GY[NE - 1] : 0.0f);
+    H00 = octet_reduce<EX>(c0, e0);
+    H01 = octet_reduce<EX>(c1, e1);
+    H11 = octet_reduce<EX>(c2, e2);
     if (H00 * H11 - H01 * H01 == 0.0f) {
       H00 = (float)((double)H00 + 1e-10);
       H11 = (float)((double)H11 + 1e-10);
@@ -160,7 +184,7 @@ __global__ void __launch_bounds__(128) k_patch_search(const PatchSearchArgs a) {
   // residue classes mod 4, so a warp-wide tap load is conflict-free whatever the patches' positions.
   float* win = smem_win + (oct >> 2) * (4 * Win<P>::SIZE) + (oct & 3);
   const int wx0 = (int)floorf(ptx) - P - 1 + pad, wy0 = (int)floorf(pty) - P - 1 + pad;  // window origin
-  {
+  if (SMEM) {
     // lane c stages columns c, c+8, c+16, ... of every window row (column clamps hoisted out of the row loop)
     constexpr int NCOL = (WIN + 7) / 8;
     const int tw1 = a.g.tw - 1, th1 = a.g.th - 1;
@@ -225,11 +249,20 @@ __global__ void __launch_bounds__(128) k_patch_search(const PatchSearchArgs a) {
 #pragma unroll
       for (int m = 0; m < M; ++m) bases[m] = wb + (prow[m] * WIN + pcol[m]) * 4;
       const float* tbase = wb + (trow * WIN + tcol) * 4;
+      // NC > 1: taps straight from the padded target image (the position is inside [lb, ub], so the
+      // p x p footprint plus its left/upper neighbours lies inside the padding)
+      const float* gb = a.I1 + (size_t)(posy + pad + LB) * pitch + (posx + pad + LB) * NC;
       float ch = 0.0f;
 #pragma unroll
       for (int i = 0; i < NE; ++i) {
-        const float* q = (i < NI) ? bases[i % M] + (i / M) * ROWS * WIN * 4 : tbase;
-        const float va = q[0], vb = q[-4], vc = q[-4 * WIN], vd = q[-4 * WIN - 4];
+        float va, vb, vc, vd;
+        if (SMEM) {
+          const float* q = (i < NI) ? bases[i % M] + (i / M) * ROWS * WIN * 4 : tbase;
+          va = q[0], vb = q[-4], vc = q[-4 * WIN], vd = q[-4 * WIN - 4];
+        } else {
+          const float* q = gb + eoff(i);
+          va = __ldg(q), vb = __ldg(q - NC), vc = __ldg(q - pitch), vd = __ldg(q - pitch - NC);
+        }
         R[i] = w0 * va + w1 * vb + w2 * vc + w3 * vd;
         if (i == 0)
           ch = R[0];
@@ -245,7 +278,7 @@ __global__ void __launch_bounds__(128) k_patch_search(const PatchSearchArgs a) {
 #pragma unroll
       for (int i = 0; i < NE; ++i) {
         float d = R[i] - m;
-        d = d - T[i];
+        d = d - (REG ? T[i] : __ldg(a.I0 + base + eoff(i)) - tmean);
         if (!L2) {
           if (a.o.costfct == 1)
             d = copysignf(sqrtf(fabsf(d)), d);
@@ -254,7 +287,8 @@ __global__ void __launch_bounds__(128) k_patch_search(const PatchSearchArgs a) {
         }
         const float ad = fabsf(d);
         R[i] = ad;
-        const float tx = GX[i] * d, ty = GY[i] * d;
+        const float tx = (REG ? GX[i] : __ldg(a.I0x + base + eoff(i))) * d;
+        const float ty = (REG ? GY[i] : __ldg(a.I0y + base + eoff(i))) * d;
         if (i == 0) {
           cgx = tx; cgy = ty; cab = ad;
         } else if (i < NI) {
@@ -303,18 +337,23 @@ int launch_p(const PatchSearchArgs& a, cudaStream_t st) {
   const int threads = 128;
   const int blocks = (a.g.nop * 8 + threads - 1) / threads;
   const size_t smem = (size_t)(threads / 8) * Win<P>::SIZE * sizeof(float);
-  if (a.o.costfct == 0)
-    k_patch_search<P, true><<<blocks, threads, smem, st>>>(a);
+  if (a.o.noc == 3) {
+    if (a.o.costfct == 0)
+      k_patch_search<P, true, 3><<<blocks, threads, 0, st>>>(a);
+    else
+      k_patch_search<P, false, 3><<<blocks, threads, 0, st>>>(a);
+  } else if (a.o.costfct == 0)
+    k_patch_search<P, true, 1><<<blocks, threads, smem, st>>>(a);
   else
-    k_patch_search<P, false><<<blocks, threads, smem, st>>>(a);
+    k_patch_search<P, false, 1><<<blocks, threads, smem, st>>>(a);
   return 0;
 }
 
 template <int P>
 void init_p() {
   const int smem = (int)((128 / 8) * Win<P>::SIZE * sizeof(float));
-  cudaFuncSetAttribute(k_patch_search<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  cudaFuncSetAttribute(k_patch_search<P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k_patch_search<P, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k_patch_search<P, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
 }  // namespace

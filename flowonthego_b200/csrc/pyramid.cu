@@ -16,6 +16,9 @@
 namespace dis {
 namespace {
 
+// NC = channels (1 grey, 3 interleaved BGR).  Every OpenCV call of ConstructImgPyramide works per channel, so
+// the colour pyramid is the grey arithmetic applied to "float columns" f = x*NC + ch of the interleaved rows.
+template <int NC>
 struct SrcU8 {
   const Mailbox* mb;
   int which;
@@ -25,32 +28,33 @@ struct SrcU8 {
     p = which ? mb->b : mb->a;
     pitch = mb->pitch;
   }
-  __device__ __forceinline__ float at(int x, int y) const {
+  __device__ __forceinline__ float at(int x, int y, int ch) const {
     int sx = min(max(x - left, 0), w_org - 1);
     int sy = min(max(y - top, 0), h_org - 1);
-    return (float)__ldg(p + (size_t)sy * pitch + sx);
+    return (float)__ldg(p + (size_t)sy * pitch + sx * NC + ch);
   }
 };
 
+template <int NC>
 struct SrcDown {  // 2x2 mean of the finer level (padded array, pad offset applied)
   const float* p;
   int pitch, pad;
   __device__ __forceinline__ void resolve() {}
-  __device__ __forceinline__ float at(int x, int y) const {
-    const float* r0 = p + (size_t)(2 * y + pad) * pitch + 2 * x + pad;
-    const float2 a = make_float2(__ldg(r0), __ldg(r0 + 1));
-    const float2 b = make_float2(__ldg(r0 + pitch), __ldg(r0 + pitch + 1));
+  __device__ __forceinline__ float at(int x, int y, int ch) const {
+    const float* r0 = p + (size_t)(2 * y + pad) * pitch + (2 * x + pad) * NC + ch;
+    const float2 a = make_float2(__ldg(r0), __ldg(r0 + NC));
+    const float2 b = make_float2(__ldg(r0 + pitch), __ldg(r0 + pitch + NC));
     return ((a.x + a.y) + (b.x + b.y)) * 0.25f;
   }
 };
 
-template <typename Src>
+template <int NC, typename Src>
 __global__ void __launch_bounds__(256) k_pyr_level(Src sa, Src sb, int w, int h, int pad, int pitch,
                                                    int tw, int th, float* Ia, float* Iax, float* Iay,
                                                    float* Ib, float* Ibx, float* Iby) {
-  const int X0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int F0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;  // first float column of this thread
   const int Y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (X0 >= pitch || Y >= th) return;
+  if (F0 >= pitch || Y >= th) return;
   const bool second = blockIdx.z == 1;
   Src s = second ? sb : sa;
   s.resolve();
@@ -62,9 +66,10 @@ __global__ void __launch_bounds__(256) k_pyr_level(Src sa, Src sb, int w, int h,
   float vi[4], vx[4], vy[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int X = X0 + k;
+    const int F = F0 + k;
+    const int X = (NC == 1) ? F : F / NC, ch = (NC == 1) ? 0 : F - X * NC;
     const int x = min(max(X - pad, 0), w - 1);
-    vi[k] = s.at(x, y);
+    vi[k] = s.at(x, y, ch);
     vx[k] = 0.0f;
     vy[k] = 0.0f;
     if (Gx != nullptr && yin && X >= pad && X < pad + w) {
@@ -73,11 +78,11 @@ __global__ void __launch_bounds__(256) k_pyr_level(Src sa, Src sb, int w, int h,
       const int xq = x == w - 1 ? (w > 1 ? w - 2 : 0) : x + 1;
       const int ym = y == 0 ? (h > 1 ? 1 : 0) : y - 1;
       const int yq = y == h - 1 ? (h > 1 ? h - 2 : 0) : y + 1;
-      vx[k] = s.at(xq, y) - s.at(xm, y);
-      vy[k] = s.at(x, yq) - s.at(x, ym);
+      vx[k] = s.at(xq, y, ch) - s.at(xm, y, ch);
+      vy[k] = s.at(x, yq, ch) - s.at(x, ym, ch);
     }
   }
-  const size_t o = (size_t)Y * pitch + X0;
+  const size_t o = (size_t)Y * pitch + F0;
   *reinterpret_cast<float4*>(I + o) = make_float4(vi[0], vi[1], vi[2], vi[3]);
   if (Gx != nullptr) {
     *reinterpret_cast<float4*>(Gx + o) = make_float4(vx[0], vx[1], vx[2], vx[3]);
@@ -85,13 +90,13 @@ __global__ void __launch_bounds__(256) k_pyr_level(Src sa, Src sb, int w, int h,
   }
 }
 
-template <typename Src>
+template <int NC, typename Src>
 void launch(Src sa, Src sb, const LevelGeom& g, float* Ia, float* Iax, float* Iay, float* Ib,
             float* Ibx, float* Iby, cudaStream_t st) {
   dim3 block(64, 4);
   dim3 grid((g.pitch / 4 + block.x - 1) / block.x, (g.th + block.y - 1) / block.y, 2);
-  k_pyr_level<Src><<<grid, block, 0, st>>>(sa, sb, g.w, g.h, g.pad, g.pitch, g.tw, g.th, Ia, Iax, Iay,
-                                           Ib, Ibx, Iby);
+  k_pyr_level<NC, Src><<<grid, block, 0, st>>>(sa, sb, g.w, g.h, g.pad, g.pitch, g.tw, g.th, Ia, Iax, Iay,
+                                               Ib, Ibx, Iby);
 }
 
 }  // namespace
@@ -109,17 +114,25 @@ void launch_set_mailbox(Mailbox* mb, const uint8_t* a, const uint8_t* b, float2*
 
 void launch_level0(const Mailbox* mb, int w_org, int h_org, int left, int top, const LevelGeom& g, float* Ia,
                    float* Iax, float* Iay, float* Ib, float* Ibx, float* Iby, cudaStream_t st) {
-  SrcU8 sa{mb, 0, nullptr, w_org, h_org, 0, left, top};
-  SrcU8 sb{mb, 1, nullptr, w_org, h_org, 0, left, top};
-  launch(sa, sb, g, Ia, Iax, Iay, Ib, Ibx, Iby, st);
+  if (g.noc == 3) {
+    SrcU8<3> sa{mb, 0, nullptr, w_org, h_org, 0, left, top}, sb{mb, 1, nullptr, w_org, h_org, 0, left, top};
+    launch<3>(sa, sb, g, Ia, Iax, Iay, Ib, Ibx, Iby, st);
+  } else {
+    SrcU8<1> sa{mb, 0, nullptr, w_org, h_org, 0, left, top}, sb{mb, 1, nullptr, w_org, h_org, 0, left, top};
+    launch<1>(sa, sb, g, Ia, Iax, Iay, Ib, Ibx, Iby, st);
+  }
 }
 
 void launch_downsample(const LevelGeom& gf, const LevelGeom& gc, const float* Ia_f, const float* Ib_f,
                        float* Ia, float* Iax, float* Iay, float* Ib, float* Ibx, float* Iby,
                        cudaStream_t st) {
-  SrcDown sa{Ia_f, gf.pitch, gf.pad};
-  SrcDown sb{Ib_f, gf.pitch, gf.pad};
-  launch(sa, sb, gc, Ia, Iax, Iay, Ib, Ibx, Iby, st);
+  if (gc.noc == 3) {
+    SrcDown<3> sa{Ia_f, gf.pitch, gf.pad}, sb{Ib_f, gf.pitch, gf.pad};
+    launch<3>(sa, sb, gc, Ia, Iax, Iay, Ib, Ibx, Iby, st);
+  } else {
+    SrcDown<1> sa{Ia_f, gf.pitch, gf.pad}, sb{Ib_f, gf.pitch, gf.pad};
+    launch<1>(sa, sb, gc, Ia, Iax, Iay, Ib, Ibx, Iby, st);
+  }
 }
 
 }  // namespace dis

@@ -45,14 +45,16 @@ constexpr float kEps = 0.001f * 0.001f;  // epsilon_color/grad/smooth, :11-14
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
 // ---- image_warp + first half of get_derivatives ------------------------------------------------
-__global__ void __launch_bounds__(256) k_warp(int w, int h, int pad, int pitch, const float* __restrict__ I0,
+// noc channels: the padded pyramid images are interleaved (copyimage de-interleaves them in the reference,
+// refine_variational.cpp:120-149); avg / Iz are written as noc planes of n = w*h floats; the mask is shared.
+__global__ void __launch_bounds__(256) k_warp(int w, int h, int pad, int pitch, int noc, const float* __restrict__ I0,
                                               const float* __restrict__ I1, const float2* __restrict__ flow,
                                               float* __restrict__ avg, float* __restrict__ Iz,
                                               float* __restrict__ mask) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   if (i >= w || j >= h) return;
-  const int o = j * w + i;
+  const int o = j * w + i, n = w * h;
   const float2 f = flow[o];
   const float xx = (float)i + f.x, yy = (float)j + f.y;
   const int x = (int)floorf(xx), y = (int)floorf(yy);
@@ -60,14 +62,16 @@ __global__ void __launch_bounds__(256) k_warp(int w, int h, int pad, int pitch, 
   const float m = (xx >= 0 && xx <= (float)(w - 1) && yy >= 0 && yy <= (float)(h - 1)) ? 1.0f : 0.0f;
   const int x1 = clampi(x, 0, w - 1), x2 = clampi(x + 1, 0, w - 1);
   const int y1 = clampi(y, 0, h - 1), y2 = clampi(y + 1, 0, h - 1);
-  const float* s = I1 + (size_t)pad * pitch + pad;
-  const float s11 = __ldg(s + (size_t)y1 * pitch + x1), s12 = __ldg(s + (size_t)y1 * pitch + x2);
-  const float s21 = __ldg(s + (size_t)y2 * pitch + x1), s22 = __ldg(s + (size_t)y2 * pitch + x2);
-  const float wv = s11 * (1.0f - dx) * (1.0f - dy) + s12 * dx * (1.0f - dy) + s21 * (1.0f - dx) * dy +
-                   s22 * dx * dy;
-  const float i0 = __ldg(I0 + (size_t)(j + pad) * pitch + i + pad);
-  avg[o] = 0.5f * (wv + i0);
-  Iz[o] = wv - i0;
+  const float* s = I1 + (size_t)pad * pitch + pad * noc;
+  for (int ch = 0; ch < noc; ++ch) {
+    const float s11 = __ldg(s + (size_t)y1 * pitch + x1 * noc + ch), s12 = __ldg(s + (size_t)y1 * pitch + x2 * noc + ch);
+    const float s21 = __ldg(s + (size_t)y2 * pitch + x1 * noc + ch), s22 = __ldg(s + (size_t)y2 * pitch + x2 * noc + ch);
+    const float wv = s11 * (1.0f - dx) * (1.0f - dy) + s12 * dx * (1.0f - dy) + s21 * (1.0f - dx) * dy +
+                     s22 * dx * dy;
+    const float i0 = __ldg(I0 + (size_t)(j + pad) * pitch + (i + pad) * noc + ch);
+    avg[(size_t)ch * n + o] = 0.5f * (wv + i0);
+    Iz[(size_t)ch * n + o] = wv - i0;
+  }
   mask[o] = m;
 }
 
@@ -113,6 +117,8 @@ __global__ void __launch_bounds__(256) k_deriv1(int w, int h, const float* __res
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   if (i >= w || j >= h) return;
   const int o = j * w + i;
+  const size_t pl = (size_t)blockIdx.z * w * h;  // colour plane
+  avg += pl; Iz += pl; Ix += pl; Iy += pl; Ixz += pl; Iyz += pl;
   Ix[o] = conv_h5(avg, w, i, j * w);
   Iy[o] = conv_v5(avg, w, h, i, j);
   Ixz[o] = conv_h5(Iz, w, i, j * w);
@@ -126,6 +132,8 @@ __global__ void __launch_bounds__(256) k_deriv2(int w, int h, const float* __res
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   if (i >= w || j >= h) return;
   const int o = j * w + i;
+  const size_t pl = (size_t)blockIdx.z * w * h;  // colour plane
+  Ix += pl; Iy += pl; Ixx += pl; Ixy += pl; Iyy += pl;
   Ixx[o] = conv_h5(Ix, w, i, j * w);
   Ixy[o] = conv_v5(Ix, w, h, i, j);
   Iyy[o] = conv_v5(Iy, w, h, i, j);
@@ -149,6 +157,7 @@ struct AssembleArgs {
   int w, h;
   float qa, hg, hd;
   int first;  // first inner iteration: uu = wx (memcpy), du = dv = 0
+  int noc;    // 1: single-channel data term; 3: RGB data term (planes of w*h floats)
   const float2* flow;  // wx, wy
   const float4* du4;   // (du,dv) records, wavefront-major
   const float *mask, *Ix, *Iy, *Iz, *Ixx, *Ixy, *Iyy, *Ixz, *Iyz;
@@ -231,41 +240,86 @@ __global__ void __launch_bounds__(ATX* ATY) k_assemble(const AssembleArgs a) {
     const float hl = (i > 0) ? s_s[ty + 1][tx] + sc : 0.0f;
     const float vt = (j > 0) ? s_s[ty][tx + 1] + sc : 0.0f;
 
-    // compute_data, 1-channel branch
+    // compute_data (opticalflow_aux.c:310-438)
     const float du = du_s[ty][tx].x, dv = du_s[ty][tx].y;
     const float mk = a.mask[o];
-    const float ix = a.Ix[o], iy = a.Iy[o], iz = a.Iz[o];
-    const float ixx = a.Ixx[o], ixy = a.Ixy[o], iyy = a.Iyy[o], ixz = a.Ixz[o], iyz = a.Iyz[o];
     float A11 = 0.0f, A12 = 0.0f, A22 = 0.0f, B1 = 0.0f, B2 = 0.0f;
-    float tmp, tmp2, n1, n2;
-    if (a.hd != 0.0f) {
-      tmp = iz + ix * du + iy * dv;
-      n1 = ix * ix + iy * iy + kDnorm;
-      tmp = mk * a.hd / sqrtf(3 * tmp * tmp / n1 + kEps);
+    if (a.noc == 1) {  // 1-channel branch
+      const float ix = a.Ix[o], iy = a.Iy[o], iz = a.Iz[o];
+      const float ixx = a.Ixx[o], ixy = a.Ixy[o], iyy = a.Iyy[o], ixz = a.Ixz[o], iyz = a.Iyz[o];
+      float tmp, tmp2, n1, n2;
+      if (a.hd != 0.0f) {
+        tmp = iz + ix * du + iy * dv;
+        n1 = ix * ix + iy * iy + kDnorm;
+        tmp = mk * a.hd / sqrtf(3 * tmp * tmp / n1 + kEps);
+        tmp /= n1;
+        A11 += tmp * ix * ix;
+        A12 += tmp * ix * iy;
+        A22 += tmp * iy * iy;
+        B1 -= tmp * iz * ix;
+        B2 -= tmp * iz * iy;
+      }
+      n1 = ixx * ixx + ixy * ixy + kDnorm;
+      n2 = iyy * iyy + ixy * ixy + kDnorm;
+      tmp = ixz + ixx * du + ixy * dv;
+      tmp2 = iyz + ixy * du + iyy * dv;
+      tmp = mk * a.hg / sqrtf(3 * tmp * tmp / n1 + 3 * tmp2 * tmp2 / n2 + kEps);
+      tmp2 = tmp / n2;
       tmp /= n1;
-      A11 += tmp * ix * ix;
-      A12 += tmp * ix * iy;
-      A22 += tmp * iy * iy;
-      B1 -= tmp * iz * ix;
-      B2 -= tmp * iz * iy;
+      A11 += tmp * ixx * ixx + tmp2 * ixy * ixy;
+      A12 += tmp * ixx * ixy + tmp2 * ixy * iyy;
+      A22 += tmp2 * iyy * iyy + tmp * ixy * ixy;
+      B1 -= tmp * ixx * ixz + tmp2 * ixy * iyz;
+      B2 -= tmp2 * iyy * iyz + tmp * ixy * ixz;
+      A11 *= 3;  // single channel only (:420-425)
+      A12 *= 3;
+      A22 *= 3;
+      B1 *= 3;
+      B2 *= 3;
+    } else {  // RGB branch: one robust weight over the three channels, no final x3
+      const size_t n = (size_t)w * h;
+      float t[6], nn[6], psi;
+      if (a.hd != 0.0f) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          const float ix = a.Ix[ch * n + o], iy = a.Iy[ch * n + o], iz = a.Iz[ch * n + o];
+          t[ch] = iz + ix * du + iy * dv;
+          nn[ch] = ix * ix + iy * iy + kDnorm;
+        }
+        psi = mk * a.hd / sqrtf(t[0] * t[0] / nn[0] + t[1] * t[1] / nn[1] + t[2] * t[2] / nn[2] + kEps);
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          const float ix = a.Ix[ch * n + o], iy = a.Iy[ch * n + o], iz = a.Iz[ch * n + o];
+          const float tc = psi / nn[ch];
+          A11 += tc * ix * ix;
+          A12 += tc * ix * iy;
+          A22 += tc * iy * iy;
+          B1 -= tc * iz * ix;
+          B2 -= tc * iz * iy;
+        }
+      }
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        const float ixx = a.Ixx[ch * n + o], ixy = a.Ixy[ch * n + o], iyy = a.Iyy[ch * n + o];
+        nn[2 * ch] = ixx * ixx + ixy * ixy + kDnorm;
+        nn[2 * ch + 1] = iyy * iyy + ixy * ixy + kDnorm;
+        t[2 * ch] = a.Ixz[ch * n + o] + ixx * du + ixy * dv;
+        t[2 * ch + 1] = a.Iyz[ch * n + o] + ixy * du + iyy * dv;
+      }
+      psi = mk * a.hg / sqrtf(t[0] * t[0] / nn[0] + t[1] * t[1] / nn[1] + t[2] * t[2] / nn[2] + t[3] * t[3] / nn[3] +
+                              t[4] * t[4] / nn[4] + t[5] * t[5] / nn[5] + kEps);
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        const float ixx = a.Ixx[ch * n + o], ixy = a.Ixy[ch * n + o], iyy = a.Iyy[ch * n + o];
+        const float ixz = a.Ixz[ch * n + o], iyz = a.Iyz[ch * n + o];
+        const float ta = psi / nn[2 * ch], tb = psi / nn[2 * ch + 1];
+        A11 += ta * ixx * ixx + tb * ixy * ixy;
+        A12 += ta * ixx * ixy + tb * ixy * iyy;
+        A22 += tb * iyy * iyy + ta * ixy * ixy;
+        B1 -= ta * ixx * ixz + tb * ixy * iyz;
+        B2 -= tb * iyy * iyz + ta * ixy * ixz;
+      }
     }
-    n1 = ixx * ixx + ixy * ixy + kDnorm;
-    n2 = iyy * iyy + ixy * ixy + kDnorm;
-    tmp = ixz + ixx * du + ixy * dv;
-    tmp2 = iyz + ixy * du + iyy * dv;
-    tmp = mk * a.hg / sqrtf(3 * tmp * tmp / n1 + 3 * tmp2 * tmp2 / n2 + kEps);
-    tmp2 = tmp / n2;
-    tmp /= n1;
-    A11 += tmp * ixx * ixx + tmp2 * ixy * ixy;
-    A12 += tmp * ixx * ixy + tmp2 * ixy * iyy;
-    A22 += tmp2 * iyy * iyy + tmp * ixy * ixy;
-    B1 -= tmp * ixx * ixz + tmp2 * ixy * iyz;
-    B2 -= tmp2 * iyy * iyz + tmp * ixy * ixz;
-    A11 *= 3;
-    A12 *= 3;
-    A22 *= 3;
-    B1 *= 3;
-    B2 *= 3;
 
     // sub_laplacian(b1, wx) and (b2, wy): horizontal pass then vertical pass, in source order
     const float2 fc = a.flow[o];
@@ -668,15 +722,15 @@ int launch_varref(const LevelGeom& g, const VarParams& v, const float* I0, const
   // algorithmic bytes per SURVEY.md section 8(d): warp+mask 28 B/px, derivative stack 40 B/px
   {
     ProfScope ps(prof, "k_warp", g.lv, 28.0 * n);
-    k_warp<<<grid, block, 0, st>>>(w, h, g.pad, g.pitch, I0, I1, flow, b.avg, b.Iz, b.mask);
+    k_warp<<<grid, block, 0, st>>>(w, h, g.pad, g.pitch, g.noc, I0, I1, flow, b.avg, b.Iz, b.mask);
   }
   {
     ProfScope ps(prof, "k_deriv1", g.lv, 24.0 * n);
-    k_deriv1<<<grid, block, 0, st>>>(w, h, b.avg, b.Iz, b.Ix, b.Iy, b.Ixz, b.Iyz);
+    k_deriv1<<<dim3(grid.x, grid.y, g.noc), block, 0, st>>>(w, h, b.avg, b.Iz, b.Ix, b.Iy, b.Ixz, b.Iyz);
   }
   {
     ProfScope ps(prof, "k_deriv2", g.lv, 16.0 * n);
-    k_deriv2<<<grid, block, 0, st>>>(w, h, b.Ix, b.Iy, b.Ixx, b.Ixy, b.Iyy);
+    k_deriv2<<<dim3(grid.x, grid.y, g.noc), block, 0, st>>>(w, h, b.Ix, b.Iy, b.Ixx, b.Ixy, b.Iyy);
   }
   launches += 3;
   if (v.n_inner <= 0) return launches;
@@ -686,7 +740,7 @@ int launch_varref(const LevelGeom& g, const VarParams& v, const float* I0, const
   varref_sizes(w, h, T, &n_coef4, &n_du4, &n_prog);
   cudaMemsetAsync(b.du4, 0, sizeof(float4) * n_du4, st);  // du = dv = 0 (image_erase, refine_variational.cpp:184-185)
   for (int it = 0; it < v.n_inner; ++it) {
-    AssembleArgs aa{w, h, v.qa, v.hg, v.hd, it == 0 ? 1 : 0, flow, b.du4,
+    AssembleArgs aa{w, h, v.qa, v.hg, v.hd, it == 0 ? 1 : 0, g.noc, flow, b.du4,
                     b.mask, b.Ix, b.Iy, b.Iz, b.Ixx, b.Ixy, b.Iyy, b.Ixz, b.Iyz, b.coefA, b.coefB, b.progress,
                     T * K};
     {

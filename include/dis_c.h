@@ -94,6 +94,11 @@ int dis_padded_size(int w, int h, int lv_f, int* w_pad, int* h_pad, int* left, i
 /* Creates an engine on CUDA device `device` with workspace for images up to max_w x max_h
  * (unpadded input size).  One handle owns one CUDA stream; several handles run concurrently. */
 int dis_create(const dis_params* params, int max_w, int max_h, int device, dis_handle** out);
+/* Same with an explicit channel count: 1 = grey (the reference's run_OF_INT build, SELECTCHANNEL=1), 3 =
+ * interleaved BGR as cv::imread(.., COLOR) delivers it (run_OF_RGB, SELECTCHANNEL=3; kroeger/run_dense.cpp:203-206,
+ * noc=3 at the engine boundary).  For 3 channels every u8 / float image argument below is interleaved and
+ * `pitch` still counts bytes per row. */
+int dis_create_c(const dis_params* params, int channels, int max_w, int max_h, int device, dis_handle** out);
 int dis_destroy(dis_handle* h);
 /* Replaces the parameter set (workspace is re-planned; fails if it no longer fits). */
 int dis_set_params(dis_handle* h, const dis_params* params);

@@ -7,8 +7,9 @@
 // Differences a caller can observe:
 //   * errors do not pass silently: OFClass::status() / OFClass::error() report them (the reference
 //     has no error channel at all);
-//   * noc must be 1 (grey; the reference's SELECTCHANNEL=1 build) and imgpadding must equal the
-//     patch size, as in the reference's only caller (kroeger/run_dense.cpp:391-400).
+//   * noc is a run-time argument here (1 = grey, 3 = interleaved BGR) whereas the reference fixes it at
+//     compile time (SELECTCHANNEL, run_OF_INT / run_OF_RGB); imgpadding must equal the patch size, as in
+//     the reference's only caller (kroeger/run_dense.cpp:391-400).
 // Link with -ldis_b200.
 #ifndef OFC_HEADER
 #define OFC_HEADER
@@ -33,9 +34,9 @@ class OFClass {
           const float tv_alpha_in, const float tv_gamma_in, const float tv_delta_in, const int tv_innerit_in,
           const int tv_solverit_in, const float tv_sor_in, const int verbosity_in, const int device = 0)
       : status_(DIS_OK) {
-    if (noc_in != 1) {
+    if (noc_in != 1 && noc_in != 3) {
       status_ = DIS_ERR_UNSUPPORTED;
-      error_ = "only noc=1 (grey images) is supported";
+      error_ = "noc must be 1 (grey) or 3 (interleaved BGR)";
       return;
     }
     dis_params p;
@@ -60,7 +61,7 @@ class OFClass {
     p.tv_sor = tv_sor_in;
     p.verbosity = verbosity_in;
     dis_handle* h = nullptr;
-    status_ = dis_create(&p, width_in, height_in, device, &h);
+    status_ = dis_create_c(&p, noc_in, width_in, height_in, device, &h);
     if (status_ != DIS_OK) {
       error_ = dis_last_error(nullptr);
       return;

@@ -58,15 +58,17 @@ _fpp = ctypes.POINTER(_fp)
 
 
 def build_pyramid(img_u8, lv_f, pad, grads=True):
-    """P1 restatement. Returns (I, Ix, Iy): lists of padded float32 arrays for levels 0..lv_f."""
+    """P1 restatement. Returns (I, Ix, Iy): lists of padded float32 arrays for levels 0..lv_f
+    (interleaved (H, W, 3) arrays for a BGR (h, w, 3) input)."""
     L = lib()
     img_u8 = np.ascontiguousarray(img_u8, np.uint8)
-    h, w = img_u8.shape
+    h, w = img_u8.shape[:2]
+    noc = 1 if img_u8.ndim == 2 else img_u8.shape[2]
     wp, hp, left, top = padded_size(w, h, lv_f)
     n = lv_f + 1
     I, Ix, Iy = (_fp * n)(), (_fp * n)(), (_fp * n)()
-    L.oracle_build_pyramid(img_u8.ctypes.data_as(ctypes.c_void_p), w, h, img_u8.strides[0], lv_f, pad,
-                           I, Ix if grads else None, Iy if grads else None)
+    L.oracle_build_pyramid_c(img_u8.ctypes.data_as(ctypes.c_void_p), w, h, img_u8.strides[0], noc, lv_f, pad,
+                             I, Ix if grads else None, Iy if grads else None)
     out = []
     for arr in (I, Ix, Iy):
         lst = []
@@ -74,7 +76,7 @@ def build_pyramid(img_u8, lv_f, pad, grads=True):
             if not arr[l]:
                 lst.append(None)
                 continue
-            shape = ((hp >> l) + 2 * pad, (wp >> l) + 2 * pad)
+            shape = ((hp >> l) + 2 * pad, (wp >> l) + 2 * pad) + ((noc,) if noc > 1 else ())
             a = np.ctypeslib.as_array(arr[l], shape=shape).copy()
             L.oracle_free(ctypes.cast(arr[l], ctypes.c_void_p))
             lst.append(a)

@@ -13,6 +13,10 @@ fixtures).
       outputs of the verbatim-compiled reference engine (oracle/_ref/libdis_ref.so) on small
       crops for parameter sets the golden file does not cover (preset 3/4 style, L1/Huber cost,
       forward-backward merging, odd patch sizes, 30-wide level).  Raw level-lv_l flow.
+  ref_cases_rgb.npz
+      the same for the reference's colour build (SELECTCHANNEL=3, oracle/_ref/libdis_ref_rgb.so): one BGR
+      crop of the two frames as cv2.imread(IMREAD_COLOR) decodes them (kroeger/run_dense.cpp:203-206),
+      stored in the file, and the raw level-lv_l flow for a few parameter sets.
 """
 import os
 import sys
@@ -45,6 +49,37 @@ CASES = [
 ]
 
 
+RGB_CROP = (40, 232, 100, 420)
+RGB_CASES = [
+    ("op2", dict(lv_f=3, lv_l=1)),
+    ("p3like", dict(lv_f=3, lv_l=1, patchsz=12, poverl=0.75, maxiter=16, miniter=16)),
+    ("notv", dict(lv_f=3, lv_l=1, usetvref=0)),
+    ("fbcon", dict(lv_f=3, lv_l=1, usefbcon=1)),
+    ("huber", dict(lv_f=3, lv_l=1, costfct=2, maxiter=24, miniter=24)),
+    ("l1_nonorm", dict(lv_f=3, lv_l=1, costfct=1, patnorm=0)),
+    ("p6", dict(lv_f=3, lv_l=1, patchsz=6, poverl=0.5)),
+    ("p10_lvl0", dict(lv_f=3, lv_l=0, patchsz=10, poverl=0.5)),
+    ("early", dict(lv_f=3, lv_l=1, miniter=2, maxiter=30, mindprate=0.2, mindrrate=0.9, minimgerr=1.0)),
+]
+
+
+def main_rgb():
+    a = cv2.imread(os.path.join(REF, "images/alley_1/frame_0001.png"), cv2.IMREAD_COLOR)
+    b = cv2.imread(os.path.join(REF, "images/alley_1/frame_0002.png"), cv2.IMREAD_COLOR)
+    y0, y1, x0, x1 = RGB_CROP
+    A, B = np.ascontiguousarray(a[y0:y1, x0:x1]), np.ascontiguousarray(b[y0:y1, x0:x1])
+    out = dict(img_a=A, img_b=B)
+    base = rd.preset_params(a.shape[1], 2)
+    for name, kw in RGB_CASES:
+        p = dict(base)
+        p.update(kw)
+        fl = rd.run_dense_ref(A, B, p, full_res=False, rgb=True)
+        out[name + "_flow"] = fl
+        out[name + "_params"] = np.array([p[k] for k in rd.PARAM_NAMES], np.float64)
+        print("rgb", name, fl.shape, float(np.abs(fl).max()))
+    np.savez_compressed(os.path.join(HERE, "ref_cases_rgb.npz"), **out)
+
+
 def main():
     a = cv2.imread(os.path.join(REF, "images/alley_1/frame_0001.png"), cv2.IMREAD_GRAYSCALE)
     b = cv2.imread(os.path.join(REF, "images/alley_1/frame_0002.png"), cv2.IMREAD_GRAYSCALE)
@@ -66,4 +101,6 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if "--rgb-only" not in sys.argv:
+        main()
+    main_rgb()

@@ -44,3 +44,11 @@ def synth_pair(w, h, seed=0, **kw):
     a = texture(w, h, seed)
     M = affine(w, h, **kw)
     return a, warp(a, M), gt_flow(w, h, M)
+
+
+def synth_pair_bgr(w, h, seed=0, **kw):
+    """Colour pair: three differently textured channels moved by the same affine flow."""
+    M = affine(w, h, **kw)
+    a = np.stack([texture(w, h, seed * 3 + k + 100) for k in range(3)], -1)
+    b = np.stack([warp(np.ascontiguousarray(a[..., k]), M) for k in range(3)], -1)
+    return np.ascontiguousarray(a), np.ascontiguousarray(b), gt_flow(w, h, M)

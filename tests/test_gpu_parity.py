@@ -12,7 +12,7 @@ import pytest
 import flowonthego_b200 as F
 from flowonthego_b200 import api
 from oracle import port, ref_driver
-from tests.synth import synth_pair
+from tests.synth import synth_pair, synth_pair_bgr
 
 pytestmark = pytest.mark.gpu
 
@@ -248,3 +248,63 @@ def test_run_dense_cli_reproduces_golden(tmp_path, golden_dir):
         assert bits_differ(F.read_flo(p), golden) == 0
     log = subprocess.run([exe, a, b, out1, "2"], capture_output=True, text=True).stdout
     assert "TIME (O.Flow Run-Time   ) (ms):" in log and "TIME (Sc: 3, #p:   448" in log
+
+
+# ---- colour mode (the reference's run_OF_RGB build, SELECTCHANNEL=3) --------------------------------------
+
+def test_rgb_reference_fixtures(golden_dir):
+    """Outputs of the verbatim-compiled RGB reference engine (tests/golden/ref_cases_rgb.npz)."""
+    z = np.load(os.path.join(golden_dir, "ref_cases_rgb.npz"))
+    A, B = z["img_a"], z["img_b"]
+    names = sorted(k[:-5] for k in z.files if k.endswith("_flow"))
+    assert len(names) >= 8
+    for name in names:
+        pd = ref_driver.parse_params(list(z[name + "_params"]))
+        with F.Engine(F.Params.from_dict(pd), A.shape[1], A.shape[0], channels=3) as e:
+            e.run_u8(A, B)
+            lvl = e.level_flow(A.shape[1], A.shape[0])
+        assert lvl.shape == z[name + "_flow"].shape, name
+        assert bits_differ(lvl, z[name + "_flow"]) == 0, name
+
+
+def test_rgb_stage_taps_bit_exact():
+    a, b, _ = synth_pair_bgr(250, 190, seed=5)
+    p = params(3, 256, lv_f=3, lv_l=0)
+    wp, hp, left, top = F.padded_size(250, 190, 3)
+    pa, pb = port.build_pyramid(a, 3, 12), port.build_pyramid(b, 3, 12)
+    fo, pf, dn = port.run_engine(pa, pb, wp, hp, p.to_dict(), taps=True, noc=3)
+    with F.Engine(p, 250, 190, channels=3) as e:
+        e.enable_taps(True)
+        full = e.run_u8(a, b)
+        for l in range(4):
+            assert bits_differ(e.tap(api.TAP_IMG_A, l), pa[0][l].ravel()) == 0
+            assert bits_differ(e.tap(api.TAP_IMG_A_DX, l), pa[1][l].ravel()) == 0
+            assert bits_differ(e.tap(api.TAP_IMG_A_DY, l), pa[2][l].ravel()) == 0
+            assert bits_differ(e.tap(api.TAP_IMG_B, l), pb[0][l].ravel()) == 0
+            assert bits_differ(e.tap(api.TAP_PATCH_FLOW, l), pf[l].ravel()) == 0
+            assert bits_differ(e.tap(api.TAP_FLOW_DENSE, l), dn[l].ravel()) == 0
+        assert bits_differ(e.level_flow(250, 190), fo) == 0
+    assert bits_differ(full, port.finish(fo, 0, left, top, 250, 190)) == 0
+
+
+def test_rgb_configs_and_engine_boundary():
+    """Patch sizes / cost functions / fb merging in colour, and the OFClass constructor with noc=3."""
+    a, b, gt = synth_pair_bgr(320, 200, seed=7)
+    for kw in (dict(patchsz=4, poverl=0.5), dict(patchsz=8, costfct=1), dict(patchsz=12, poverl=0.75, costfct=2),
+               dict(patchsz=14, poverl=0.5, patnorm=0), dict(patchsz=16, poverl=0.5, usefbcon=1)):
+        p = params(2, 1024, lv_f=3, lv_l=1, **kw)
+        with F.Engine(p, 320, 200, channels=3) as e:
+            flow = e.run_u8(a, b)
+        assert_flow_parity(flow, port.run_u8(a, b, p.to_dict()), p.patchsz, 1)
+    m = 16
+    assert np.abs(flow - gt)[m:-m, m:-m].mean() < 0.25
+    p = params(2, 1024, lv_f=3, lv_l=1)
+    pa, pb = port.build_pyramid(a, 3, 8), port.build_pyramid(b, 3, 8)
+    out = np.zeros((100, 160, 2), np.float32)
+    F.OFClass(*pa, *pb, 8, out, None, 320, 200, 3, 1, p.maxiter, p.miniter, p.mindprate, p.mindrrate, p.minimgerr,
+              8, p.poverl, False, 0, 3, 1, True, p.tv_alpha, p.tv_gamma, p.tv_delta, p.tv_innerit, p.tv_solverit,
+              p.tv_sor, 0)
+    assert bits_differ(out, port.run_engine(pa, pb, 320, 200, p.to_dict(), noc=3)) == 0
+    with pytest.raises(ValueError):
+        with F.Engine(p, 320, 200, channels=3) as e:
+            e.run_u8(a[..., 0], b[..., 0])  # grey input on a colour engine

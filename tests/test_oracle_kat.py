@@ -42,6 +42,19 @@ def test_reference_fixtures_bit_exact(alley_pair, golden_dir):
         assert bits_differ(lvl, z[name + "_flow"]) == 0, name
 
 
+def test_reference_fixtures_rgb_bit_exact(golden_dir):
+    """Colour build (SELECTCHANNEL=3): raw engine output of the verbatim-compiled RGB reference."""
+    z = np.load(os.path.join(golden_dir, "ref_cases_rgb.npz"))
+    A, B = z["img_a"], z["img_b"]
+    names = sorted(k[:-5] for k in z.files if k.endswith("_flow"))
+    assert len(names) >= 8
+    for name in names:
+        p = ref_driver.parse_params(list(z[name + "_params"]))
+        _, lvl = port.run_u8(A, B, p, want_level=True)
+        assert lvl.shape == z[name + "_flow"].shape, name
+        assert bits_differ(lvl, z[name + "_flow"]) == 0, name
+
+
 def test_pyramid_matches_opencv(alley_pair):
     """P1 restatement vs the cv2 call sequence of ConstructImgPyramide (kroeger/run_dense.cpp:130-178)."""
     a, _ = alley_pair
