@@ -1,7 +1,7 @@
 """flowonthego_b200 -- B200-native Dense Inverse Search optical flow (drop-in for the hot path of
 zhaorz/FlowOnTheGo's CPU reference `kroeger/`).  See DESIGN.md and include/dis_c.h."""
-from .api import (DisError, Engine, OFClass, Params, PARAM_NAMES, lib, padded_size, pinned_empty, read_flo, read_image_gray,
+from .api import (DisError, Engine, OFClass, Params, PARAM_NAMES, lib, padded_size, pinned_empty, read_flo, read_image_bgr, read_image_gray,
                   run_dense, write_flo)
 
 __all__ = ["DisError", "Engine", "OFClass", "Params", "PARAM_NAMES", "lib", "padded_size", "pinned_empty",
-           "read_flo", "read_image_gray", "run_dense", "write_flo"]
+           "read_flo", "read_image_bgr", "read_image_gray", "run_dense", "write_flo"]

@@ -120,6 +120,7 @@ def lib():
         L.dis_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
         L.dis_host_free.argtypes = [vp]
         L.dis_read_image_gray.argtypes = [ctypes.c_char_p, vp, ctypes.c_size_t, ctypes.POINTER(ip), ctypes.POINTER(ip)]
+        L.dis_read_image_bgr.argtypes = L.dis_read_image_gray.argtypes
         L.dis_write_flo.argtypes = [ctypes.c_char_p, fp, ip, ip]
         L.dis_read_flo.argtypes = [ctypes.c_char_p, fp, ctypes.c_size_t, ctypes.POINTER(ip), ctypes.POINTER(ip)]
         _LIB = L
@@ -342,18 +343,30 @@ def read_image_gray(path):
     return out
 
 
-def run_dense(img1, img2, outfile, *args, device=0):
+def read_image_bgr(path):
+    """PNG / PGM / PPM -> BGR u8 (h, w, 3) like cv2.imread(.., IMREAD_COLOR) (kroeger/run_dense.cpp:203-206)."""
+    w, h = ctypes.c_int(), ctypes.c_int()
+    _check(lib().dis_read_image_bgr(os.fsencode(path), None, 0, ctypes.byref(w), ctypes.byref(h)), None)
+    out = np.empty((h.value, w.value, 3), np.uint8)
+    _check(lib().dis_read_image_bgr(os.fsencode(path), out.ctypes.data, out.size, ctypes.byref(w), ctypes.byref(h)), None)
+    return out
+
+
+def run_dense(img1, img2, outfile, *args, device=0, channels=1):
     """``run_dense img1 img2 out [X | 20 params]`` -- the reference CLI variants (kroeger/README.md:48-88).
     img1/img2 are file names (PNG/PGM/PPM, decoded natively to the same grey values as the
-    reference's cv::imread(.., GRAYSCALE), kroeger/run_dense.cpp:208-209) or decoded grey u8 arrays."""
+    reference's cv::imread(.., GRAYSCALE), kroeger/run_dense.cpp:208-209) or decoded grey u8 arrays;
+    channels=3 is the reference's colour binary run_OF_RGB (BGR decode, kroeger/run_dense.cpp:203-206)."""
     def load(x):
-        return x if isinstance(x, np.ndarray) else read_image_gray(x)
+        if isinstance(x, np.ndarray):
+            return x
+        return read_image_bgr(x) if channels == 3 else read_image_gray(x)
     a, b = load(img1), load(img2)
     if len(args) <= 1:
         p = Params.preset(int(args[0]) if args else 2, a.shape[1], verbosity=2)
     else:
         p = Params.from_argv(args)
-    with Engine(p, a.shape[1], a.shape[0], device) as e:
+    with Engine(p, a.shape[1], a.shape[0], device, channels=channels) as e:
         flow = e.run_u8(a, b)
     if outfile is not None:
         write_flo(outfile, flow)

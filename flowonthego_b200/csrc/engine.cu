@@ -924,6 +924,23 @@ int dis_read_image_gray(const char* path, uint8_t* out, size_t cap, int* w, int*
   return DIS_OK;
 }
 
+int dis_read_image_bgr(const char* path, uint8_t* out, size_t cap, int* w, int* h) {
+  if (!path || !w || !h) return DIS_ERR_INVALID_ARG;
+  GrayImage g;
+  const std::string err = read_image(path, 3, &g);
+  if (!err.empty()) {
+    g_create_error = err;
+    return DIS_ERR_IO;
+  }
+  *w = g.w;
+  *h = g.h;
+  if (out) {
+    if (cap < g.px.size()) return DIS_ERR_INVALID_ARG;
+    memcpy(out, g.px.data(), g.px.size());
+  }
+  return DIS_OK;
+}
+
 int dis_write_flo(const char* path, const float* flow_uv, int w, int h) {
   if (!path || !flow_uv || w <= 0 || h <= 0) return DIS_ERR_INVALID_ARG;
   FILE* f = fopen(path, "wb");

@@ -28,7 +28,7 @@ inline uint8_t gray_cv(int r, int g, int b) { return (uint8_t)((b * 1868 + g * 9
 // cv2.imread(IMREAD_GRAYSCALE) (OpenCV 4.13) on the reference's RGB frames images/alley_1/*.png.
 inline uint8_t gray_png(int r, int g, int b) { return (uint8_t)((9797 * r + 19234 * g + 3737 * b) >> 15); }
 
-std::string read_pnm(const std::vector<uint8_t>& d, GrayImage* out) {
+std::string read_pnm(const std::vector<uint8_t>& d, int want, GrayImage* out) {
   size_t p = 2;
   auto next_int = [&](int* v) {
     while (p < d.size()) {
@@ -55,18 +55,25 @@ std::string read_pnm(const std::vector<uint8_t>& d, GrayImage* out) {
   if (w <= 0 || h <= 0 || p + need > d.size()) return "truncated PNM";
   out->w = w;
   out->h = h;
-  out->px.resize((size_t)w * h);
-  if (!color) {
-    memcpy(out->px.data(), d.data() + p, need);
-  } else {
-    for (size_t i = 0; i < (size_t)w * h; ++i) out->px[i] = gray_cv(d[p + 3 * i], d[p + 3 * i + 1], d[p + 3 * i + 2]);
+  out->ch = want;
+  out->px.resize((size_t)w * h * want);
+  const uint8_t* q = d.data() + p;
+  if (want == 1) {
+    if (!color) {
+      memcpy(out->px.data(), q, need);
+    } else {
+      for (size_t i = 0; i < (size_t)w * h; ++i) out->px[i] = gray_cv(q[3 * i], q[3 * i + 1], q[3 * i + 2]);
+    }
+  } else {  // BGR like cv::imread(.., IMREAD_COLOR)
+    for (size_t i = 0; i < (size_t)w * h; ++i)
+      for (int k = 0; k < 3; ++k) out->px[3 * i + k] = color ? q[3 * i + 2 - k] : q[i];
   }
   return "";
 }
 
 uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
 
-std::string read_png(const std::vector<uint8_t>& d, GrayImage* out) {
+std::string read_png(const std::vector<uint8_t>& d, int want, GrayImage* out) {
   static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
   if (d.size() < 33 || memcmp(d.data(), sig, 8)) return "not a PNG";
   size_t p = 8;
@@ -135,9 +142,22 @@ std::string read_png(const std::vector<uint8_t>& d, GrayImage* out) {
   }
   out->w = w;
   out->h = h;
-  out->px.resize((size_t)w * h);
+  out->ch = want;
+  out->px.resize((size_t)w * h * want);
   for (size_t i = 0; i < (size_t)w * h; ++i) {
     const uint8_t* q = &img[i * ch];
+    if (want == 3) {  // BGR like cv::imread(.., IMREAD_COLOR): alpha dropped, grey replicated
+      uint8_t* o = &out->px[3 * i];
+      switch (ctype) {
+        case 0: case 4: o[0] = o[1] = o[2] = q[0]; break;
+        case 2: case 6: o[0] = q[2]; o[1] = q[1]; o[2] = q[0]; break;
+        case 3:
+          if ((size_t)q[0] * 3 + 2 >= plte.size()) return "PNG palette index out of range";
+          o[0] = plte[q[0] * 3 + 2]; o[1] = plte[q[0] * 3 + 1]; o[2] = plte[q[0] * 3];
+          break;
+      }
+      continue;
+    }
     switch (ctype) {
       case 0: case 4: out->px[i] = q[0]; break;
       case 2: case 6: out->px[i] = gray_png(q[0], q[1], q[2]); break;
@@ -153,10 +173,13 @@ std::string read_png(const std::vector<uint8_t>& d, GrayImage* out) {
 
 }  // namespace
 
-std::string read_gray_image(const char* path, GrayImage* out) {
+std::string read_gray_image(const char* path, GrayImage* out) { return read_image(path, 1, out); }
+
+std::string read_image(const char* path, int channels, GrayImage* out) {
+  if (channels != 1 && channels != 3) return "channels must be 1 or 3";
   std::vector<uint8_t> d;
   if (!read_file(path, &d)) return std::string("cannot read ") + path;
-  if (d.size() > 2 && d[0] == 'P' && (d[1] == '5' || d[1] == '6')) return read_pnm(d, out);
-  if (d.size() > 8 && d[0] == 0x89 && d[1] == 'P') return read_png(d, out);
+  if (d.size() > 2 && d[0] == 'P' && (d[1] == '5' || d[1] == '6')) return read_pnm(d, channels, out);
+  if (d.size() > 8 && d[0] == 0x89 && d[1] == 'P') return read_png(d, channels, out);
   return "unsupported image format (PNG, PGM and PPM are read natively; convert others first)";
 }

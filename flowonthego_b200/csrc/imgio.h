@@ -8,9 +8,12 @@
 #include <vector>
 
 struct GrayImage {
-  int w = 0, h = 0;
-  std::vector<uint8_t> px;  // row-major, pitch == w
+  int w = 0, h = 0, ch = 1;
+  std::vector<uint8_t> px;  // row-major, pitch == w * ch; ch == 3: interleaved BGR
 };
 
 // Returns empty string on success, otherwise the reason.
 std::string read_gray_image(const char* path, GrayImage* out);
+// channels = 1: as above; channels = 3: BGR as cv::imread(.., CV_LOAD_IMAGE_COLOR) delivers it for the
+// reference's colour build (kroeger/run_dense.cpp:203-206): alpha dropped, grey files replicated.
+std::string read_image(const char* path, int channels, GrayImage* out);

@@ -3,6 +3,8 @@
 //   run_dense img1 img2 out.flo                      operating point 2, coarsest scale chosen automatically
 //   run_dense img1 img2 out.flo X                    operating point X = 1..4
 //   run_dense img1 img2 out.flo p1 ... p20           all parameters explicit (order of run_dense.cpp:271-291)
+// Built twice like the reference (kroeger/CMakeLists.txt: run_OF_INT with SELECTCHANNEL=1, run_OF_RGB with
+// SELECTCHANNEL=3): run_dense reads the images as grey, run_dense_rgb as BGR colour.
 // Everything between image decode and SaveFlowFile runs on the GPU (dis_run_u8).  Timing lines follow
 // the reference's format when verbosity > 0 / > 1.
 #include <sys/time.h>
@@ -13,6 +15,10 @@
 
 #include "dis_c.h"
 #include "imgio.h"
+
+#ifndef SELECTCHANNEL
+#define SELECTCHANNEL 1
+#endif
 
 static double now_ms() {
   timeval tv;
@@ -30,8 +36,8 @@ int main(int argc, char** argv) {
   }
   double t0 = now_ms();
   GrayImage a, b;
-  std::string err = read_gray_image(argv[1], &a);
-  if (err.empty()) err = read_gray_image(argv[2], &b);
+  std::string err = read_image(argv[1], SELECTCHANNEL, &a);
+  if (err.empty()) err = read_image(argv[2], SELECTCHANNEL, &b);
   if (!err.empty()) {
     fprintf(stderr, "run_dense: %s\n", err.c_str());
     return 1;
@@ -50,13 +56,13 @@ int main(int argc, char** argv) {
   if (p.verbosity > 1) printf("TIME (Image loading     ) (ms): %3g\n", now_ms() - t0);
 
   dis_handle* h = nullptr;
-  if (dis_create(&p, a.w, a.h, 0, &h) != DIS_OK) {
+  if (dis_create_c(&p, SELECTCHANNEL, a.w, a.h, 0, &h) != DIS_OK) {
     fprintf(stderr, "run_dense: %s\n", dis_last_error(nullptr));
     return 1;
   }
   if (p.verbosity > 1) dis_enable_stage_timing(h, 1);
   std::vector<float> flow((size_t)a.w * a.h * 2);
-  if (dis_run_u8(h, a.px.data(), b.px.data(), a.w, a.h, a.w, flow.data()) != DIS_OK) {
+  if (dis_run_u8(h, a.px.data(), b.px.data(), a.w, a.h, a.w * SELECTCHANNEL, flow.data()) != DIS_OK) {
     fprintf(stderr, "run_dense: %s\n", dis_last_error(h));
     dis_destroy(h);
     return 1;

@@ -164,6 +164,8 @@ int dis_read_flo(const char* path, float* flow_uv, size_t n_floats, int* w, int*
 /* Reads an 8-bit PNG / PGM / PPM as grey (OpenCV's grey conversion reproduced bit for bit).  With
  * out == NULL only *w,*h are filled. */
 int dis_read_image_gray(const char* path, uint8_t* out, size_t cap, int* w, int* h);
+/* Colour build (kroeger/run_dense.cpp:203-206 cv::imread(.., COLOR)): interleaved BGR, 3*w*h bytes. */
+int dis_read_image_bgr(const char* path, uint8_t* out, size_t cap, int* w, int* h);
 
 /* ---- stage-level debug taps (tests only; never on the timed path) ---------------------- */
 typedef enum dis_tap {

@@ -308,3 +308,24 @@ def test_rgb_configs_and_engine_boundary():
     with pytest.raises(ValueError):
         with F.Engine(p, 320, 200, channels=3) as e:
             e.run_u8(a[..., 0], b[..., 0])  # grey input on a colour engine
+
+
+def test_rgb_cli(tmp_path, golden_dir):
+    """run_dense_rgb (= the reference's run_OF_RGB binary): native BGR decode of a PPM + colour engine."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(F.api.__file__), "run_dense_rgb")
+    z = np.load(os.path.join(golden_dir, "ref_cases_rgb.npz"))
+    A, B = z["img_a"], z["img_b"]
+    names = []
+    for name, img in (("a.ppm", A), ("b.ppm", B)):
+        names.append(str(tmp_path / name))
+        with open(names[-1], "wb") as f:
+            f.write(b"P6\n%d %d\n255\n" % (img.shape[1], img.shape[0]))
+            f.write(np.ascontiguousarray(img[..., ::-1]).tobytes())  # PPM stores RGB
+        assert np.array_equal(F.read_image_bgr(names[-1]), img)
+    argv = "3 1 12 12 0.05 0.95 0 8 0.40 0 1 0 1 10 10 5 1 3 1.6 0".split()
+    out = str(tmp_path / "rgb.flo")
+    subprocess.check_call([exe, names[0], names[1], out] + argv)
+    pd = ref_driver.parse_params(argv)
+    assert bits_differ(F.read_flo(out), port.run_u8(A, B, pd)) == 0
+    assert bits_differ(F.run_dense(names[0], names[1], None, *argv, channels=3), port.run_u8(A, B, pd)) == 0
