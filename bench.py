@@ -185,7 +185,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=128, help="frame pairs per step per GPU")
-    ap.add_argument("--streams", type=int, default=32, help="engine instances (CUDA streams) per GPU")
+    ap.add_argument("--streams", type=int, default=64, help="engine instances (CUDA streams) per GPU")
     ap.add_argument("--no-extra", action="store_true", help="skip the 4K (C4a) side measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
