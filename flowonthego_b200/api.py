@@ -121,6 +121,10 @@ def lib():
         L.dis_host_free.argtypes = [vp]
         L.dis_read_image_gray.argtypes = [ctypes.c_char_p, vp, ctypes.c_size_t, ctypes.POINTER(ip), ctypes.POINTER(ip)]
         L.dis_read_image_bgr.argtypes = L.dis_read_image_gray.argtypes
+        L.dis_flow_to_color.argtypes = [fp, ip, ip, ctypes.c_float, ip, vp, fp]
+        L.dis_flow_epe.argtypes = [fp, fp, ip, ip, ip, ip, ctypes.POINTER(ctypes.c_double),
+                                   ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]
+        L.dis_write_png_bgr.argtypes = [ctypes.c_char_p, vp, ip, ip]
         L.dis_write_flo.argtypes = [ctypes.c_char_p, fp, ip, ip]
         L.dis_read_flo.argtypes = [ctypes.c_char_p, fp, ctypes.c_size_t, ctypes.POINTER(ip), ctypes.POINTER(ip)]
         _LIB = L
@@ -350,6 +354,36 @@ def read_image_bgr(path):
     out = np.empty((h.value, w.value, 3), np.uint8)
     _check(lib().dis_read_image_bgr(os.fsencode(path), out.ctypes.data, out.size, ctypes.byref(w), ctypes.byref(h)), None)
     return out
+
+
+def flow_to_color(flow, maxmotion=-1.0, device=0, want_stats=False):
+    """Middlebury colour coding on the GPU (flow_code/C/color_flow.cpp MotionToColor): (h, w, 2) float32 ->
+    (h, w, 3) u8 in B,G,R order [and dict(maxrad, minu, maxu, minv, maxv)]."""
+    flow = np.ascontiguousarray(flow, np.float32)
+    h, w = flow.shape[:2]
+    out = np.empty((h, w, 3), np.uint8)
+    st = np.zeros(5, np.float32)
+    _check(lib().dis_flow_to_color(_as_fp(flow), w, h, float(maxmotion), int(device), out.ctypes.data, _as_fp(st)), None)
+    if want_stats:
+        return out, dict(zip(("maxrad", "minu", "maxu", "minv", "maxv"), map(float, st)))
+    return out
+
+
+def flow_epe(flow_a, flow_b, margin=0, device=0):
+    """(mean, max, count) of the endpoint error |a - b|_2 on the GPU, border margin excluded."""
+    a = np.ascontiguousarray(flow_a, np.float32)
+    b = np.ascontiguousarray(flow_b, np.float32)
+    if a.shape != b.shape or a.ndim != 3 or a.shape[2] != 2:
+        raise ValueError("need two (h, w, 2) flow fields of identical shape")
+    mean, mx, cnt = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+    _check(lib().dis_flow_epe(_as_fp(a), _as_fp(b), a.shape[1], a.shape[0], int(margin), int(device),
+                              ctypes.byref(mean), ctypes.byref(mx), ctypes.byref(cnt)), None)
+    return mean.value, mx.value, cnt.value
+
+
+def write_png_bgr(path, bgr):
+    bgr = np.ascontiguousarray(bgr, np.uint8)
+    _check(lib().dis_write_png_bgr(os.fsencode(path), bgr.ctypes.data, bgr.shape[1], bgr.shape[0]), None)
 
 
 def run_dense(img1, img2, outfile, *args, device=0, channels=1):

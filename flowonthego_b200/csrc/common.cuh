@@ -101,6 +101,16 @@ struct VarRefBuffers {
 int launch_varref(const LevelGeom& g, const VarParams& v, const float* I0, const float* I1,
                   float2* flow, const VarRefBuffers& b, cudaStream_t st, Prof* prof = nullptr);
 void varref_sizes(int w, int h, int n_solver, size_t* n_coef4, size_t* n_du4, size_t* n_prog);
+// engine.cu: error text returned by dis_last_error(NULL) (handle-less entry points)
+void set_global_error(const char* fmt, ...);
+// flowviz.cu
+void flowviz_init_device();
+void launch_flow_color(const float2* d_flow, int w, int h, float maxmotion, uint8_t* d_bgr, unsigned* d_stats,
+                       cudaStream_t st);
+void decode_flow_stats(const unsigned* h_stats, float out[5]);
+int flow_epe_blocks();
+void launch_flow_epe(const float2* d_a, const float2* d_b, int w, int h, int margin, double* d_psum, float* d_pmax,
+                     unsigned long long* d_pcnt, cudaStream_t st);
 // finish.cu
 void launch_finish(const float2* flow_l, int wl, int hl, int lv_l, int left, int top, int w_org,
                    int h_org, const Mailbox* mb, cudaStream_t st);

@@ -143,6 +143,21 @@ int fail(dis_handle* h, int code, const char* fmt, ...) {
   return code;
 }
 
+}  // namespace
+
+namespace dis {
+void set_global_error(const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_create_error = buf;
+}
+}  // namespace dis
+
+namespace {
+
 #define CU(h, call)                                                                           \
   do {                                                                                        \
     cudaError_t e_ = (call);                                                                  \
@@ -685,6 +700,7 @@ int dis_create_c(const dis_params* params, int channels, int max_w, int max_h, i
     return DIS_ERR_CUDA;
   }
   patch_search_init_device();
+  flowviz_init_device();
   varref_init_device();
   rc = plan(h, max_w, max_h);
   if (rc != DIS_OK) {

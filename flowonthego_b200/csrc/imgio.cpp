@@ -173,6 +173,52 @@ std::string read_png(const std::vector<uint8_t>& d, int want, GrayImage* out) {
 
 }  // namespace
 
+std::string write_png_bgr(const char* path, const uint8_t* bgr, int w, int h) {
+  // scanlines: filter byte 0 + RGB
+  const size_t stride = (size_t)w * 3 + 1;
+  std::vector<uint8_t> raw(stride * h);
+  for (int y = 0; y < h; ++y) {
+    uint8_t* r = &raw[stride * y];
+    *r++ = 0;
+    const uint8_t* s = bgr + (size_t)y * w * 3;
+    for (int x = 0; x < w; ++x, s += 3, r += 3) {
+      r[0] = s[2];
+      r[1] = s[1];
+      r[2] = s[0];
+    }
+  }
+  uLongf zlen = compressBound((uLong)raw.size());
+  std::vector<uint8_t> z(zlen);
+  if (compress2(z.data(), &zlen, raw.data(), (uLong)raw.size(), 6) != Z_OK) return "PNG deflate failed";
+  FILE* f = fopen(path, "wb");
+  if (!f) return std::string("cannot write ") + path;
+  auto put32 = [](uint8_t* p, uint32_t v) { p[0] = v >> 24; p[1] = v >> 16; p[2] = v >> 8; p[3] = v; };
+  bool ok = true;
+  auto chunk = [&](const char* type, const uint8_t* data, size_t len) {
+    uint8_t hd[8];
+    put32(hd, (uint32_t)len);
+    memcpy(hd + 4, type, 4);
+    uint32_t crc = crc32(0, hd + 4, 4);
+    if (len) crc = crc32(crc, data, (uInt)len);
+    uint8_t tail[4];
+    put32(tail, crc);
+    ok = ok && fwrite(hd, 1, 8, f) == 8 && (len == 0 || fwrite(data, 1, len, f) == len) && fwrite(tail, 1, 4, f) == 4;
+  };
+  static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+  ok = fwrite(sig, 1, 8, f) == 8;
+  uint8_t ihdr[13];
+  put32(ihdr, (uint32_t)w);
+  put32(ihdr + 4, (uint32_t)h);
+  ihdr[8] = 8;   // bit depth
+  ihdr[9] = 2;   // colour type RGB
+  ihdr[10] = ihdr[11] = ihdr[12] = 0;
+  chunk("IHDR", ihdr, 13);
+  chunk("IDAT", z.data(), zlen);
+  chunk("IEND", nullptr, 0);
+  ok = (fclose(f) == 0) && ok;
+  return ok ? "" : std::string("short write to ") + path;
+}
+
 std::string read_gray_image(const char* path, GrayImage* out) { return read_image(path, 1, out); }
 
 std::string read_image(const char* path, int channels, GrayImage* out) {

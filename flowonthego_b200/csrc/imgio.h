@@ -17,3 +17,5 @@ std::string read_gray_image(const char* path, GrayImage* out);
 // channels = 1: as above; channels = 3: BGR as cv::imread(.., CV_LOAD_IMAGE_COLOR) delivers it for the
 // reference's colour build (kroeger/run_dense.cpp:203-206): alpha dropped, grey files replicated.
 std::string read_image(const char* path, int channels, GrayImage* out);
+// 8-bit RGB PNG from interleaved BGR pixels (what flow_code/C/imageLib/ImageIOpng.cpp writes for color_flow).
+std::string write_png_bgr(const char* path, const uint8_t* bgr, int w, int h);

@@ -167,6 +167,25 @@ int dis_read_image_gray(const char* path, uint8_t* out, size_t cap, int* w, int*
 /* Colour build (kroeger/run_dense.cpp:203-206 cv::imread(.., COLOR)): interleaved BGR, 3*w*h bytes. */
 int dis_read_image_bgr(const char* path, uint8_t* out, size_t cap, int* w, int* h);
 
+/* ---- evaluation tools behind the path (flow_code/C) ----------------------------------------- */
+/* Middlebury colour coding of a flow field on the GPU: replaces MotionToColor (flow_code/C/color_flow.cpp:19-71)
+ * with computeColor (flow_code/C/colorcode.cpp:53-77).  maxmotion <= 0: normalise by the largest motion present.
+ * bgr_out: w*h*3 bytes, interleaved B,G,R (the byte order computeColor stores).  stats_out (optional, 5 floats):
+ * max radius, min u, max u, min v, max v -- the numbers color_flow prints.  Unknown flow (|u| or |v| > 1e9, NaN;
+ * flow_code/C/flowIO.cpp:35-39) is black.  Host buffers; runs on CUDA device `device`. */
+int dis_flow_to_color(const float* flow_uv, int w, int h, float maxmotion, int device, uint8_t* bgr_out,
+                      float* stats_out);
+/* Device-resident variant for pipelines: d_stats is 5 words of device scratch; asynchronous on `stream`
+ * (a cudaStream_t).  dis_create must have run on the device (it uploads the colour wheel). */
+int dis_flow_to_color_device(const float* d_flow_uv, int w, int h, float maxmotion, uint8_t* d_bgr,
+                             uint32_t* d_stats, void* stream);
+/* Endpoint error between two flow fields on the GPU: mean and max of |a - b|_2 over the pixels at least
+ * `margin` away from the border where both flows are known; computed in double, deterministic. */
+int dis_flow_epe(const float* flow_a, const float* flow_b, int w, int h, int margin, int device, double* mean_out,
+                 double* max_out, long long* count_out);
+/* 8-bit RGB PNG from interleaved BGR pixels (the output format of color_flow). */
+int dis_write_png_bgr(const char* path, const uint8_t* bgr, int w, int h);
+
 /* ---- stage-level debug taps (tests only; never on the timed path) ---------------------- */
 typedef enum dis_tap {
   DIS_TAP_IMG_A = 0,   /* padded pyramid image a, level l: (w_l+2p) x (h_l+2p)         */

@@ -13,6 +13,9 @@ fixtures).
       outputs of the verbatim-compiled reference engine (oracle/_ref/libdis_ref.so) on small
       crops for parameter sets the golden file does not cover (preset 3/4 style, L1/Huber cost,
       forward-backward merging, odd patch sizes, 30-wide level).  Raw level-lv_l flow.
+  alley_0001_color.png
+      kroeger/flows/alley_0001.png, the reference's colour coding of alley_0001.flo (flow_code/C/color_flow),
+      pixel for pixel (re-encoded) -- the known-answer vector of the colour-coding tool.
   ref_cases_rgb.npz
       the same for the reference's colour build (SELECTCHANNEL=3, oracle/_ref/libdis_ref_rgb.so): one BGR
       crop of the two frames as cv2.imread(IMREAD_COLOR) decodes them (kroeger/run_dense.cpp:203-206),
@@ -87,6 +90,8 @@ def main():
     cv2.imwrite(os.path.join(HERE, "alley_0002_gray.png"), b, [cv2.IMWRITE_PNG_COMPRESSION, 9])
     g = rd.read_flo(os.path.join(REF, "kroeger/flows/alley_0001.flo"))
     np.savez_compressed(os.path.join(HERE, "alley_0001_flo.npz"), flow=g)
+    col = cv2.imread(os.path.join(REF, "kroeger/flows/alley_0001.png"), cv2.IMREAD_COLOR)
+    cv2.imwrite(os.path.join(HERE, "alley_0001_color.png"), col, [cv2.IMWRITE_PNG_COMPRESSION, 9])
     out = {}
     base = rd.preset_params(a.shape[1], 2)
     for name, (y0, y1, x0, x1), kw in CASES:
