@@ -121,6 +121,12 @@ def lib():
         L.dis_host_free.argtypes = [vp]
         L.dis_read_image_gray.argtypes = [ctypes.c_char_p, vp, ctypes.c_size_t, ctypes.POINTER(ip), ctypes.POINTER(ip)]
         L.dis_read_image_bgr.argtypes = L.dis_read_image_gray.argtypes
+        L.dis_video_create.argtypes = [pp, ip, ip, ip, ip, ip, ctypes.POINTER(vp)]
+        L.dis_video_destroy.argtypes = [vp]
+        L.dis_video_destroy.restype = None
+        L.dis_video_push.argtypes = [vp, vp, ip, fp]
+        L.dis_video_pop.argtypes = [vp, ctypes.POINTER(fp)]
+        L.dis_video_pending.argtypes = [vp]
         L.dis_flow_to_color.argtypes = [fp, ip, ip, ctypes.c_float, ip, vp, fp]
         L.dis_flow_epe.argtypes = [fp, fp, ip, ip, ip, ip, ctypes.POINTER(ctypes.c_double),
                                    ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]
@@ -301,6 +307,76 @@ class Engine:
     @property
     def stream(self):
         return lib().dis_stream(self._h)
+
+
+class FlowStream:
+    """Video-stream front end (dis_video_*): push consecutive frames, get one flow per consecutive pair,
+    `depth` pairs in flight on the GPU, every frame uploaded once.  Each flow equals Engine.run_u8 on that
+    pair bit for bit."""
+
+    def __init__(self, params, w, h, depth=8, device=0, channels=1):
+        self._v = ctypes.c_void_p()
+        self.params = params if isinstance(params, Params) else Params.from_dict(params)
+        self.w, self.h, self.depth, self.channels = int(w), int(h), int(depth), int(channels)
+        _check(lib().dis_video_create(ctypes.byref(self.params), self.channels, self.w, self.h, int(device),
+                                      self.depth, ctypes.byref(self._v)), None)
+        shape = (self.h, self.w) if self.channels == 1 else (self.h, self.w, self.channels)
+        self._frames = [pinned_empty(shape, np.uint8) for _ in range(self.depth + 1)]
+        self._flows = [pinned_empty((self.h, self.w, 2), np.float32) for _ in range(self.depth)]
+        self._n = 0
+
+    def close(self):
+        if self._v:
+            lib().dis_video_destroy(self._v)
+            self._v = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def pending(self):
+        return lib().dis_video_pending(self._v)
+
+    def push(self, frame):
+        """Enqueue the next frame.  Requires pending < depth (pop first otherwise)."""
+        stage = self._frames[self._n % (self.depth + 1)]
+        if frame.shape != stage.shape:
+            raise ValueError("frame shape %s, expected %s" % (frame.shape, stage.shape))
+        if self._n and self.pending >= self.depth:
+            raise DisError(2, "%d pairs in flight, pop one first" % self.depth)
+        stage[...] = frame
+        out = _as_fp(self._flows[(self._n - 1) % self.depth]) if self._n else None
+        _check(lib().dis_video_push(self._v, stage.ctypes.data, stage.strides[0], out), None)
+        self._n += 1
+
+    def pop(self):
+        """Wait for the oldest pair in flight; returns its flow (a view of a pinned buffer that is reused
+        `depth` pairs later -- copy it to keep it)."""
+        p = _fp()
+        _check(lib().dis_video_pop(self._v, ctypes.byref(p)), None)
+        addr = ctypes.cast(p, ctypes.c_void_p).value
+        for f in self._flows:
+            if f.ctypes.data == addr:
+                return f
+        raise DisError(1, "dis_video_pop returned an unknown buffer")
+
+    def flows(self, frames):
+        """Generator: flow of every consecutive pair of the iterable `frames` (copies)."""
+        for fr in frames:
+            if self.pending >= self.depth:
+                yield self.pop().copy()
+            self.push(fr)
+        while self.pending > 0:
+            yield self.pop().copy()
 
 
 def OFClass(im_ao, im_ao_dx, im_ao_dy, im_bo, im_bo_dx, im_bo_dy, imgpadding, outflow, initflow, width, height,

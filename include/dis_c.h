@@ -167,6 +167,21 @@ int dis_read_image_gray(const char* path, uint8_t* out, size_t cap, int* w, int*
 /* Colour build (kroeger/run_dense.cpp:203-206 cv::imread(.., COLOR)): interleaved BGR, 3*w*h bytes. */
 int dis_read_image_bgr(const char* path, uint8_t* out, size_t cap, int* w, int* h);
 
+/* ---- video-stream front end ------------------------------------------------------------------ */
+/* Consecutive frames in, one flow field per consecutive pair out (the loop the reference's CUDA twin runs over a
+ * video, src/main.cpp; kroeger/run_dense.cpp itself handles one pair per process).  `depth` pairs are in flight
+ * on `depth` engine handles; every frame is uploaded once.  Each flow is bit-identical to dis_run_u8 on that
+ * pair.  Usage: push frame 0 (flow_out ignored), then for every further frame push(frame, flow_out) -- when
+ * dis_video_pending() == depth, pop first.  dis_video_pop waits for the OLDEST pair in flight and returns the
+ * flow_out pointer it was given.  Host buffers should be pinned (dis_host_alloc) and must stay valid until
+ * popped.  Not thread-safe per object. */
+typedef struct dis_video dis_video;
+int dis_video_create(const dis_params* params, int channels, int w, int h, int device, int depth, dis_video** out);
+void dis_video_destroy(dis_video* v);
+int dis_video_push(dis_video* v, const uint8_t* frame, int pitch, float* flow_out);
+int dis_video_pop(dis_video* v, float** flow_out);
+int dis_video_pending(const dis_video* v);
+
 /* ---- evaluation tools behind the path (flow_code/C) ----------------------------------------- */
 /* Middlebury colour coding of a flow field on the GPU: replaces MotionToColor (flow_code/C/color_flow.cpp:19-71)
  * with computeColor (flow_code/C/colorcode.cpp:53-77).  maxmotion <= 0: normalise by the largest motion present.
