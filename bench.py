@@ -310,6 +310,41 @@ def main():
     ms_e = timed(lambda: step_host(), Ke)
     e2e_value = N * B * Ke / (ms_e / 1e3)
 
+    # ---- side measurement: the same host-buffer workload through the video front end (dis_video_*: every frame
+    # uploaded once, pairs pipelined over S handles)
+    stream_extra = None
+    if rank == 0 and N == 1 and not args.no_extra:
+        try:
+            import ctypes
+            L = F.lib()
+            vid = ctypes.c_void_p()
+            rc = L.dis_video_create(ctypes.byref(p), 1, W1080, H1080, local_rank, S, ctypes.byref(vid))
+            if rc != 0:
+                raise RuntimeError(L.dis_last_error(None).decode())
+            fp = ctypes.POINTER(ctypes.c_float)
+
+            def step_video():
+                L.dis_video_push(vid, h_frames[0].ctypes.data, W1080, None)
+                for i in range(B):
+                    if L.dis_video_pending(vid) >= S:
+                        L.dis_video_pop(vid, None)
+                    if L.dis_video_push(vid, h_frames[i + 1].ctypes.data, W1080, h_out[i % S].ctypes.data_as(fp)) != 0:
+                        raise RuntimeError(L.dis_last_error(None).decode())
+                while L.dis_video_pending(vid) > 0:
+                    L.dis_video_pop(vid, None)
+
+            step_video()
+            t0 = time.perf_counter()
+            for _ in range(Ke):
+                step_video()
+            dt = time.perf_counter() - t0
+            L.dis_video_destroy(vid)
+            stream_extra = {"value": B * Ke / dt, "unit": UNIT, "h2d_bytes_per_step": W1080 * H1080 * (B + 1),
+                            "d2h_bytes_per_step": 8 * W1080 * H1080 * B, "pairs_in_flight": S,
+                            "how": "dis_video_push/pop with pinned host frames and flow buffers, host wall clock"}
+        except Exception as ex:
+            stream_extra = {"error": repr(ex)}
+
     # ---- results are only *gathered* over NCCL (no data-path collective): per-pair flow summaries of the
     # last S pairs of every rank go to rank 0
     from flowonthego_b200 import shard
@@ -415,6 +450,8 @@ def main():
             line["cpu_baseline"] = cpu_base
         if extra is not None:
             line["extra_c4a_4k"] = extra
+        if stream_extra is not None:
+            line["extra_video_stream_e2e"] = stream_extra
         print(json.dumps(line))
     for e in engines:
         e.close()

@@ -275,6 +275,7 @@ class Engine:
 
     # ---- introspection ------------------------------------------------------------------------
     def enable_taps(self, on=True):
+        """True/1: all pyramid levels built level by level; 2: the product's pyramid path (levels >= lv_l only)."""
         _check(lib().dis_enable_taps(self._h, int(on)), self._h)
 
     def enable_stage_timing(self, on=True):

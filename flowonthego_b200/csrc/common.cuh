@@ -61,6 +61,9 @@ void launch_set_mailbox(Mailbox* mb, const uint8_t* a, const uint8_t* b, float2*
 void launch_level0(const Mailbox* mb, int w_org, int h_org,
                    int left, int top, const LevelGeom& g, float* Ia, float* Iax, float* Iay,
                    float* Ib, float* Ibx, float* Iby, cudaStream_t st);
+void launch_first_level(const Mailbox* mb, int L, int w_org, int h_org, int left, int top, const LevelGeom& g,
+                        float* bm_a, float* bm_b, float* Ia, float* Iax, float* Iay, float* Ib, float* Ibx, float* Iby,
+                        cudaStream_t st);
 void launch_downsample(const LevelGeom& gf, const LevelGeom& gc, const float* Ia_f, const float* Ib_f,
                        float* Ia, float* Iax, float* Iay, float* Ib, float* Ibx, float* Iby,
                        cudaStream_t st);

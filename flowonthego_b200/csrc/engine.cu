@@ -108,6 +108,7 @@ struct dis_handle {
   VarRefBuffers vb{};
   float2* d_out = nullptr;
   Mailbox* mailbox = nullptr;
+  float *bm_a = nullptr, *bm_b = nullptr;  // block-mean scratch of the first processed level (lv_l > 0)
   char* slab = nullptr;
   size_t slab_bytes = 0;
 
@@ -118,7 +119,7 @@ struct dis_handle {
 
   // timing / taps
   bool stage_timing = false;
-  bool taps = false;
+  int taps = 0;  // 1: all pyramid levels built the reference's way; 2: the product pyramid path, taps of its levels
   bool kprof_on = false;
   KernelProf kprof;
   std::vector<std::vector<Tap>> tapdata;  // [tap][level]
@@ -245,6 +246,8 @@ size_t carve(dis_handle* h, int w, int h_img, char* base, bool assign) {
     }
   }
   const LevelGeom& gf = lv[q.lv_l].g;  // finest processed level = largest buffers
+  float* bm_a = c.take<float>((size_t)gf.w * gf.h * h->noc);
+  float* bm_b = c.take<float>((size_t)gf.w * gf.h * h->noc);
   float2* pflow = c.take<float2>(gf.nop);
   float* pweight = c.take<float>((size_t)gf.nop * h->opt.novals);
   float2* pflow_bw = nullptr;
@@ -270,9 +273,11 @@ size_t carve(dis_handle* h, int w, int h_img, char* base, bool assign) {
     vb.progress = c.take<int>(n_prog);
   }
   float2* d_out = c.take<float2>((size_t)w * h_img);
-  Mailbox* mailbox = c.take<Mailbox>(1);
+  Mailbox* mailbox = c.take<Mailbox>(2);  // [1]: scratch target of the debug launches
   if (assign) {
     h->mailbox = mailbox;
+    h->bm_a = bm_a;
+    h->bm_b = bm_b;
     h->lv = lv;
     h->d_a = d_a;
     h->d_b = d_b;
@@ -352,13 +357,23 @@ void tap_image(dis_handle* h, int tap, int level, const float* d, const LevelGeo
 // stage 1 (kroeger/run_dense.cpp:298-344): pyramids of both frames from the u8 inputs
 int enqueue_pyramids(dis_handle* h) {
   const dis_params& q = h->P;
-  for (int l = 0; l <= q.lv_f; ++l) {
+  // Product path: nothing reads the levels below lv_l (the engine starts at lv_l, oflow.cpp:199), so the first
+  // processed level is built straight from the u8 frames (bit-identical, see k_block_mean) and the finer levels are
+  // not materialised.  With taps enabled (tests) every level is built the reference's way so that it can be compared.
+  const int first = (h->taps == 1 || q.lv_l > 8) ? 0 : q.lv_l;
+  for (int l = first; l <= q.lv_f; ++l) {
     LevelBufs& L = h->lv[l];
     // SURVEY 8(d) B_P: u8 in (level 0 only), I of both frames out, Ix/Iy of frame a on used levels
-    const double np_ = (double)L.g.tw * L.g.th;
-    ProfScope ps(h->kprof_on ? &h->kprof : nullptr, l == 0 ? "k_pyr_level0" : "k_pyr_down", l,
-                 (l == 0 ? 2.0 * h->w_org * h->h_org : 0.0) + 8.0 * np_ + (l >= q.lv_l ? 8.0 * np_ : 0.0));
-    if (l == 0)
+    double np_ = (double)L.g.tw * L.g.th;
+    if (l == first)
+      for (int k = 0; k < first; ++k) np_ += (double)h->lv[k].g.tw * h->lv[k].g.th;  // the model counts all levels
+    ProfScope ps(h->kprof_on ? &h->kprof : nullptr, l == first ? "k_pyr_level0" : "k_pyr_down", l,
+                 (l == first ? 2.0 * h->w_org * h->h_org : 0.0) + 8.0 * np_ + (l >= q.lv_l ? 8.0 * np_ : 0.0));
+    if (l == first && first > 0) {
+      launch_first_level(h->mailbox, first, h->w_org, h->h_org, h->left, h->top, L.g, h->bm_a, h->bm_b, L.Ia, L.Iax,
+                         L.Iay, L.Ib, L.Ibx, L.Iby, h->stream);
+      h->launches++;
+    } else if (l == 0)
       launch_level0(h->mailbox, h->w_org, h->h_org, h->left, h->top, L.g, L.Ia, L.Iax, L.Iay, L.Ib,
                     L.Ibx, L.Iby, h->stream);
     else
@@ -367,7 +382,7 @@ int enqueue_pyramids(dis_handle* h) {
     h->launches++;
   }
   if (h->taps)
-    for (int l = 0; l <= q.lv_f; ++l) {
+    for (int l = first; l <= q.lv_f; ++l) {
       LevelBufs& L = h->lv[l];
       tap_image(h, DIS_TAP_IMG_A, l, L.Ia, L.g);
       tap_image(h, DIS_TAP_IMG_A_DX, l, L.Iax, L.g);
@@ -493,6 +508,8 @@ int enqueue_finish(dis_handle* h) {
                8.0 * (double)L.g.w * L.g.h + 8.0 * (double)h->w_org * h->h_org);
   launch_finish(L.flow, L.g.w, L.g.h, h->P.lv_l, h->left, h->top, h->w_org, h->h_org, h->mailbox, h->stream);
   h->launches++;
+  if (const char* dbg = getenv("DIS_DEBUG_EXTRA_LAUNCHES"))  // experiment: cost of a kernel launch at throughput
+    for (int i = 0, n = atoi(dbg); i < n; ++i) launch_set_mailbox(h->mailbox + 1, nullptr, nullptr, nullptr, 0, h->stream);
   CU(h, cudaGetLastError());
   return DIS_OK;
 }
@@ -748,7 +765,7 @@ int dis_enable_stage_timing(dis_handle* h, int on) {
 
 int dis_enable_taps(dis_handle* h, int on) {
   if (!h) return DIS_ERR_INVALID_ARG;
-  h->taps = on != 0;
+  h->taps = on == 2 ? 2 : (on != 0);
   if (!on) h->tapdata.clear();
   return DIS_OK;
 }

@@ -48,6 +48,55 @@ struct SrcDown {  // 2x2 mean of the finer level (padded array, pad offset appli
   }
 };
 
+template <int NC>
+struct SrcPlain {  // unpadded level image (output of k_block_mean)
+  const float* p;
+  int w;
+  __device__ __forceinline__ void resolve() {}
+  __device__ __forceinline__ float at(int x, int y, int ch) const { return __ldg(p + ((size_t)y * w + x) * NC + ch); }
+};
+
+// Level L (1 <= L <= 8) straight from the u8 frames: the 2x2 box means of levels 1..L telescope into the mean of a
+// 2^L x 2^L block, and every partial sum of the reference's ((a+b)+(c+d))*0.25 chain is exact in fp32 (values are
+// multiples of 4^-(l-1) below 256: 8+2l-1 <= 24 significant bits), so float(sum of the block) * 4^-L is bit-identical
+// to the level-by-level result.  The block is taken from the replicate-padded level-0 image (run_dense.cpp:298-311),
+// i.e. source coordinates are clamped.  Saves writing and re-reading the levels below lv_l that nothing else uses.
+template <int NC>
+__global__ void __launch_bounds__(256) k_block_mean(const Mailbox* __restrict__ mb, int L, int w_org, int h_org,
+                                                    int left, int top, int w, int h, float* __restrict__ out_a,
+                                                    float* __restrict__ out_b) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= w || y >= h) return;
+  const uint8_t* __restrict__ src = blockIdx.z ? mb->b : mb->a;
+  float* __restrict__ out = blockIdx.z ? out_b : out_a;
+  const int pitch = mb->pitch, B = 1 << L;
+  const int x0 = x * B - left, y0 = y * B - top;
+  unsigned acc[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) acc[c] = 0;
+  const bool inside = x0 >= 0 && y0 >= 0 && x0 + B <= w_org && y0 + B <= h_org;
+  for (int dy = 0; dy < B; ++dy) {
+    const int sy = min(max(y0 + dy, 0), h_org - 1);
+    const uint8_t* row = src + (size_t)sy * pitch;
+    if (inside && NC == 1 && B >= 4 && (((size_t)(row + x0)) & 3) == 0) {
+      for (int dx = 0; dx < B; dx += 4) {  // aligned interior: 4 pixels per load
+        const uchar4 v = __ldg(reinterpret_cast<const uchar4*>(row + x0 + dx));
+        acc[0] += (unsigned)v.x + v.y + v.z + v.w;
+      }
+    } else {
+      for (int dx = 0; dx < B; ++dx) {
+        const int sx = min(max(x0 + dx, 0), w_org - 1);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[c] += __ldg(row + sx * NC + c);
+      }
+    }
+  }
+  const float scale = 1.0f / (float)(1u << (2 * L));  // power of two: exact
+#pragma unroll
+  for (int c = 0; c < NC; ++c) out[((size_t)y * w + x) * NC + c] = (float)acc[c] * scale;
+}
+
 template <int NC, typename Src>
 __global__ void __launch_bounds__(256) k_pyr_level(Src sa, Src sb, int w, int h, int pad, int pitch,
                                                    int tw, int th, float* Ia, float* Iax, float* Iay,
@@ -119,6 +168,23 @@ void launch_level0(const Mailbox* mb, int w_org, int h_org, int left, int top, c
     launch<3>(sa, sb, g, Ia, Iax, Iay, Ib, Ibx, Iby, st);
   } else {
     SrcU8<1> sa{mb, 0, nullptr, w_org, h_org, 0, left, top}, sb{mb, 1, nullptr, w_org, h_org, 0, left, top};
+    launch<1>(sa, sb, g, Ia, Iax, Iay, Ib, Ibx, Iby, st);
+  }
+}
+
+// First processed level L = lv_l > 0 of the product path: block means from the u8 frames into the scratch images
+// bm_a / bm_b (g.w x g.h x noc floats), then the padded image + gradients from those.
+void launch_first_level(const Mailbox* mb, int L, int w_org, int h_org, int left, int top, const LevelGeom& g,
+                        float* bm_a, float* bm_b, float* Ia, float* Iax, float* Iay, float* Ib, float* Ibx, float* Iby,
+                        cudaStream_t st) {
+  dim3 block(32, 8), grid((g.w + 31) / 32, (g.h + 7) / 8, 2);
+  if (g.noc == 3) {
+    k_block_mean<3><<<grid, block, 0, st>>>(mb, L, w_org, h_org, left, top, g.w, g.h, bm_a, bm_b);
+    SrcPlain<3> sa{bm_a, g.w}, sb{bm_b, g.w};
+    launch<3>(sa, sb, g, Ia, Iax, Iay, Ib, Ibx, Iby, st);
+  } else {
+    k_block_mean<1><<<grid, block, 0, st>>>(mb, L, w_org, h_org, left, top, g.w, g.h, bm_a, bm_b);
+    SrcPlain<1> sa{bm_a, g.w}, sb{bm_b, g.w};
     launch<1>(sa, sb, g, Ia, Iax, Iay, Ib, Ibx, Iby, st);
   }
 }

@@ -213,7 +213,9 @@ typedef enum dis_tap {
   DIS_TAP_IMG_B_DX = 7,
   DIS_TAP_IMG_B_DY = 8
 } dis_tap;
-/* Keeps per-level copies of the tapped buffers during the next runs (costs memory and time). */
+/* Keeps per-level copies of the tapped buffers during the next runs (costs memory and time).  on = 1: every
+ * pyramid level 0..lv_f is built level by level like ConstructImgPyramide; on = 2: the pyramid is built as on the
+ * untapped path (levels below lv_l are skipped, see pyramid.cu) and only levels >= lv_l can be fetched. */
 int dis_enable_taps(dis_handle* h, int on);
 int dis_fetch_tap(dis_handle* h, int tap, int level, float* out, size_t n_floats, size_t* n_written);
 

@@ -104,6 +104,25 @@ def test_stage_taps_bit_exact():
     assert bits_differ(full, port.finish(fo, 0, left, top, 250, 190)) == 0
 
 
+def test_product_pyramid_path_bit_exact():
+    """Untapped runs build level lv_l straight from the u8 frames (k_block_mean) and skip the finer levels: the
+    images and gradients the engine sees must still be those of ConstructImgPyramide, for every lv_l, odd sizes
+    (divisibility padding -> clamped blocks) and colour."""
+    for (w, h, lv_f, lv_l, ch) in ((250, 190, 3, 2, 1), (322, 198, 4, 1, 1), (256, 192, 3, 3, 1), (250, 190, 3, 2, 3),
+                                   (1000, 600, 5, 4, 1)):
+        a, b, _ = (synth_pair if ch == 1 else synth_pair_bgr)(w, h, seed=w)
+        p = params(2, 1024, lv_f=lv_f, lv_l=lv_l)
+        pa, pb = port.build_pyramid(a, lv_f, 8), port.build_pyramid(b, lv_f, 8)
+        with F.Engine(p, w, h, channels=ch) as e:
+            e.enable_taps(2)
+            e.run_u8(a, b)
+            for l in range(lv_l, lv_f + 1):
+                assert bits_differ(e.tap(api.TAP_IMG_A, l), pa[0][l].ravel()) == 0, (w, l)
+                assert bits_differ(e.tap(api.TAP_IMG_A_DX, l), pa[1][l].ravel()) == 0, (w, l)
+                assert bits_differ(e.tap(api.TAP_IMG_A_DY, l), pa[2][l].ravel()) == 0, (w, l)
+                assert bits_differ(e.tap(api.TAP_IMG_B, l), pb[0][l].ravel()) == 0, (w, l)
+
+
 def test_engine_boundary_run_pyramids(alley_pair):
     """dis_run_pyramids == OFC::OFClass ctor (kroeger/oflow.h:84-111): caller-built (OpenCV) pyramids in,
     level-lv_l flow out; also through the Python OFClass mirror with the reference's argument list."""
