@@ -8,7 +8,7 @@ w, h = 1920, 1080
 p = F.Params.preset(3, 1920, verbosity=0)
 a, b, _ = synth_pair(w, h, seed=1)
 da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
-for S in (1, 2, 4, 8, 12, 16, 24, 32, 48):
+for S in (16, 32, 64, 96, 128, 192, 256):
     engs = [F.Engine(p, w, h) for _ in range(S)]
     do = torch.empty((S, h, w, 2), dtype=torch.float32, device="cuda")
     for i, e in enumerate(engs):
