@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libdis_b200.so")
+_LIB_PATH = os.environ.get("DIS_B200_LIB") or os.path.join(_HERE, "libdis_b200.so")  # override: experiments only
 _LIB = None
 
 PARAM_NAMES = ("lv_f", "lv_l", "maxiter", "miniter", "mindprate", "mindrrate", "minimgerr", "patchsz",
@@ -103,6 +103,7 @@ def lib():
         L.dis_create_c.argtypes = [pp, ip, ip, ip, ip, ctypes.POINTER(vp)]
         L.dis_destroy.argtypes = [vp]
         L.dis_set_params.argtypes = [vp, pp]
+        L.dis_set_option.argtypes = [vp, ip, ip]
         L.dis_run_pyramids.argtypes = [vp] + [fpp] * 6 + [ip, ip, ip, fp, fp]
         L.dis_run_u8.argtypes = [vp, vp, vp, ip, ip, ip, fp]
         L.dis_submit_u8.argtypes = [vp, vp, vp, ip, ip, ip, fp]
@@ -121,6 +122,15 @@ def lib():
         L.dis_host_free.argtypes = [vp]
         L.dis_read_image_gray.argtypes = [ctypes.c_char_p, vp, ctypes.c_size_t, ctypes.POINTER(ip), ctypes.POINTER(ip)]
         L.dis_read_image_bgr.argtypes = L.dis_read_image_gray.argtypes
+        L.dis_group_create.argtypes = [pp, ip, ip, ip, ip, ip, ctypes.POINTER(vp)]
+        L.dis_group_destroy.argtypes = [vp]
+        L.dis_group_destroy.restype = None
+        L.dis_group_submit_u8_device.argtypes = [vp, ip, ctypes.POINTER(vp), ctypes.POINTER(vp), ip, ip, ip, ctypes.POINTER(vp)]
+        L.dis_group_wait.argtypes = [vp]
+        L.dis_group_stream.argtypes = [vp]
+        L.dis_group_stream.restype = vp
+        L.dis_group_last_error.argtypes = [vp]
+        L.dis_group_last_error.restype = ctypes.c_char_p
         L.dis_video_create.argtypes = [pp, ip, ip, ip, ip, ip, ctypes.POINTER(vp)]
         L.dis_video_destroy.argtypes = [vp]
         L.dis_video_destroy.restype = None
@@ -173,6 +183,9 @@ def pinned_empty(shape, dtype):
 _PINNED = {}
 
 
+OPT_SOR_GROUP, OPT_USE_GRAPH = 1, 2
+
+
 class Engine:
     """One engine instance = one dis_handle (stream, workspace, CUDA graph)."""
 
@@ -206,6 +219,10 @@ class Engine:
     def set_params(self, params):
         self.params = params if isinstance(params, Params) else Params.from_dict(params)
         _check(lib().dis_set_params(self._h, ctypes.byref(self.params)), self._h)
+
+    def set_option(self, option, value):
+        """OPT_SOR_GROUP (8 | 16), OPT_USE_GRAPH (0 | 1); results never change."""
+        _check(lib().dis_set_option(self._h, int(option), int(value)), self._h)
 
     # ---- whole run_dense data path ----------------------------------------------------------
     def run_u8(self, a, b, out=None):
@@ -308,6 +325,51 @@ class Engine:
     @property
     def stream(self):
         return lib().dis_stream(self._h)
+
+
+class EngineGroup:
+    """n pairs per graph launch (dis_group_*): device-resident frames in, device-resident flows out."""
+
+    def __init__(self, params, max_w, max_h, n, device=0, channels=1):
+        self._g = ctypes.c_void_p()
+        self.params = params if isinstance(params, Params) else Params.from_dict(params)
+        self.n = int(n)
+        _check(lib().dis_group_create(ctypes.byref(self.params), int(channels), int(max_w), int(max_h), int(device),
+                                      self.n, ctypes.byref(self._g)), None)
+
+    def close(self):
+        if self._g:
+            lib().dis_group_destroy(self._g)
+            self._g = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _err(self, rc):
+        if rc != 0:
+            raise DisError(rc, (lib().dis_group_last_error(self._g) or b"").decode())
+
+    def submit_u8_device(self, d_a, d_b, w, h, pitch, d_flow):
+        """d_a, d_b, d_flow: sequences of device pointers (ints), one per pair (at most n)."""
+        k = len(d_a)
+        arr = ctypes.c_void_p * k
+        self._err(lib().dis_group_submit_u8_device(self._g, k, arr(*d_a), arr(*d_b), w, h, pitch, arr(*d_flow)))
+
+    def wait(self):
+        self._err(lib().dis_group_wait(self._g))
+
+    @property
+    def stream(self):
+        return lib().dis_group_stream(self._g)
 
 
 class FlowStream:

@@ -32,6 +32,7 @@ struct OptParams {
 struct VarParams {  // kroeger/refine_variational.cpp:28-42
   float qa, hg, hd, omega;
   int n_inner, n_solver;
+  int sor_group;  // 8 or 16: k_sor_wavefront instantiation (DIS_OPT_SOR_GROUP)
 };
 
 // Optional per-kernel profiling hook (CUDA events around every launch; used by bench.py's roofline

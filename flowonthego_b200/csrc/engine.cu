@@ -114,6 +114,7 @@ struct dis_handle {
 
   // graph
   bool use_graph = true;
+  int sor_group = 0;  // DIS_OPT_SOR_GROUP: 0 auto, 8, 16
   cudaGraphExec_t graph_exec = nullptr;
   int graph_w = 0, graph_h = 0;
 
@@ -431,6 +432,10 @@ int enqueue_engine(dis_handle* h, const float2* d_initflow) {
   vp.hd = q.tv_delta * 0.5f / 3.0f;
   vp.omega = q.tv_sor;
   vp.n_solver = q.tv_solverit;
+  {  // auto: a fine level that fills the GPU by itself (4K at lv_l = 0) prefers the low-latency instantiation
+    const LevelGeom& gfin = h->lv[q.lv_l].g;
+    vp.sor_group = h->sor_group ? h->sor_group : ((size_t)gfin.w * gfin.h >= (1u << 20) ? 16 : 8);
+  }
   Prof* prof = h->kprof_on ? &h->kprof : nullptr;
   for (int sl = q.lv_f; sl >= q.lv_l; --sl) {
     LevelBufs& L = h->lv[sl];
@@ -740,6 +745,26 @@ int dis_destroy(dis_handle* h) {
   return DIS_OK;
 }
 
+int dis_set_option(dis_handle* h, int option, int value) {
+  if (!h) return DIS_ERR_INVALID_ARG;
+  switch (option) {
+    case DIS_OPT_SOR_GROUP:
+      if (value != 0 && value != 8 && value != 16) return fail(h, DIS_ERR_INVALID_ARG, "DIS_OPT_SOR_GROUP must be 0, 8 or 16");
+      if (value != h->sor_group) {
+        CU(h, cudaSetDevice(h->device));
+        CU(h, cudaStreamSynchronize(h->stream));
+        drop_graph(h);
+        h->sor_group = value;
+      }
+      return DIS_OK;
+    case DIS_OPT_USE_GRAPH:
+      h->use_graph = value != 0;
+      return DIS_OK;
+    default:
+      return fail(h, DIS_ERR_INVALID_ARG, "unknown option %d", option);
+  }
+}
+
 int dis_set_params(dis_handle* h, const dis_params* params) {
   if (!h) return DIS_ERR_INVALID_ARG;
   char why[128];
@@ -811,6 +836,145 @@ int dis_host_alloc(void** ptr, size_t bytes) {
   return cudaHostAlloc(ptr, bytes, cudaHostAllocDefault) == cudaSuccess ? DIS_OK : DIS_ERR_NOMEM;
 }
 int dis_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? DIS_OK : DIS_ERR_CUDA; }
+
+// ---- groups: n pairs per graph launch ---------------------------------------------------------------------
+// A pair is a chain of ~90 dependent launches, most of them latency-bound (SOR wavefronts, coarse levels), and
+// the device exposes at most 32 hardware work queues, so with one pair per stream about 32 chains are in flight
+// and throughput = 32 / chain latency, well before the SMs are full (tools/stage_cost2.py: one more SOR sweep
+// costs exactly its latency / 32).  A group records the runs of n handles as n parallel branches of ONE graph
+// (fork/join through events during capture) and launches it on the first member's stream: n times as many
+// chains per queue, same kernels, same results.
+struct dis_group {
+  std::vector<dis_handle*> m;
+  cudaGraphExec_t graph_exec = nullptr;
+  int graph_w = 0, graph_h = 0, graph_n = 0;
+  int device = 0;
+  std::string err;
+};
+
+namespace {
+int gfail(dis_group* g, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (g) g->err = buf;
+  g_create_error = buf;
+  return code;
+}
+#define CUGR(g, call)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess)                                                                              \
+      return gfail(g, DIS_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+}  // namespace
+
+int dis_group_create(const dis_params* params, int channels, int max_w, int max_h, int device, int n, dis_group** out) {
+  if (!out || n < 1 || n > 64) return gfail(nullptr, DIS_ERR_INVALID_ARG, "dis_group_create: bad argument");
+  *out = nullptr;
+  dis_group* g = new dis_group;
+  g->device = device;
+  for (int i = 0; i < n; ++i) {
+    dis_handle* h = nullptr;
+    const int rc = dis_create_c(params, channels, max_w, max_h, device, &h);
+    if (rc != DIS_OK) {
+      dis_group_destroy(g);
+      return rc;
+    }
+    g->m.push_back(h);
+  }
+  *out = g;
+  return DIS_OK;
+}
+
+void dis_group_destroy(dis_group* g) {
+  if (!g) return;
+  cudaSetDevice(g->device);
+  if (!g->m.empty()) cudaStreamSynchronize(g->m[0]->stream);
+  if (g->graph_exec) cudaGraphExecDestroy(g->graph_exec);
+  for (dis_handle* h : g->m) dis_destroy(h);
+  delete g;
+}
+
+int dis_group_size(const dis_group* g) { return g ? (int)g->m.size() : 0; }
+const char* dis_group_last_error(const dis_group* g) { return g ? g->err.c_str() : g_create_error.c_str(); }
+void* dis_group_stream(dis_group* g) { return g && !g->m.empty() ? g->m[0]->stream : nullptr; }
+
+int dis_group_submit_u8_device(dis_group* g, int n, const uint8_t* const* d_a, const uint8_t* const* d_b, int w,
+                               int h_img, int pitch, float* const* d_flow) {
+  if (!g || !d_a || !d_b || !d_flow || n < 1 || n > (int)g->m.size())
+    return gfail(g, DIS_ERR_INVALID_ARG, "dis_group_submit_u8_device: bad argument");
+  CUGR(g, cudaSetDevice(g->device));
+  cudaStream_t lead = g->m[0]->stream;
+  bool replanned = false;
+  for (int i = 0; i < n; ++i) {
+    dis_handle* h = g->m[i];
+    if (!d_a[i] || !d_b[i] || !d_flow[i] || pitch < w * h->noc) return gfail(g, DIS_ERR_INVALID_ARG, "bad pair %d", i);
+    if (h->taps || h->stage_timing || h->kprof_on) return gfail(g, DIS_ERR_UNSUPPORTED, "taps/profiling need single handles");
+    replanned |= !(w == h->w_org && h_img == h->h_org && !h->lv.empty());
+    const int rc = plan(h, w, h_img);
+    if (rc != DIS_OK) return gfail(g, rc, "%s", h->err.c_str());
+  }
+  if (replanned) {
+    for (int i = 0; i < n; ++i) CUGR(g, cudaStreamSynchronize(g->m[i]->stream));  // workspace memsets of plan()
+    if (g->graph_exec) {
+      cudaGraphExecDestroy(g->graph_exec);
+      g->graph_exec = nullptr;
+    }
+  }
+  for (int i = 0; i < n; ++i)
+    launch_set_mailbox(g->m[i]->mailbox, d_a[i], d_b[i], reinterpret_cast<float2*>(d_flow[i]), pitch, lead);
+  if (!(g->graph_exec && g->graph_w == w && g->graph_h == h_img && g->graph_n == n)) {
+    if (g->graph_exec) {
+      cudaGraphExecDestroy(g->graph_exec);
+      g->graph_exec = nullptr;
+    }
+    std::vector<cudaEvent_t> ev(n);
+    for (auto& e : ev) CUGR(g, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CUGR(g, cudaStreamBeginCapture(lead, cudaStreamCaptureModeThreadLocal));
+    CUGR(g, cudaEventRecord(ev[0], lead));
+    for (int i = 1; i < n; ++i) CUGR(g, cudaStreamWaitEvent(g->m[i]->stream, ev[0], 0));  // fork
+    int rc = DIS_OK;
+    for (int i = 0; i < n && rc == DIS_OK; ++i) {
+      dis_handle* h = g->m[i];
+      h->launches = 1;
+      rc = enqueue_pyramids(h);
+      if (rc == DIS_OK) rc = enqueue_engine(h, nullptr);
+      if (rc == DIS_OK) rc = enqueue_finish(h);
+      h->tm.launches = h->launches;
+    }
+    for (int i = 1; i < n; ++i) {  // join
+      cudaEventRecord(ev[i], g->m[i]->stream);
+      cudaStreamWaitEvent(lead, ev[i], 0);
+    }
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(lead, &graph);
+    for (auto& x : ev) cudaEventDestroy(x);
+    if (rc != DIS_OK || e != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      return gfail(g, rc != DIS_OK ? rc : DIS_ERR_CUDA, "group capture failed: %s",
+                   rc != DIS_OK ? "enqueue error" : cudaGetErrorString(e));
+    }
+    const cudaError_t e2 = cudaGraphInstantiate(&g->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e2 != cudaSuccess) return gfail(g, DIS_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e2));
+    g->graph_w = w;
+    g->graph_h = h_img;
+    g->graph_n = n;
+  }
+  CUGR(g, cudaGraphLaunch(g->graph_exec, lead));
+  return DIS_OK;
+}
+
+int dis_group_wait(dis_group* g) {
+  if (!g || g->m.empty()) return DIS_ERR_INVALID_ARG;
+  CUGR(g, cudaSetDevice(g->device));
+  CUGR(g, cudaStreamSynchronize(g->m[0]->stream));
+  CUGR(g, cudaGetLastError());
+  return DIS_OK;
+}
 
 int dis_submit_u8_device(dis_handle* h, const uint8_t* d_a, const uint8_t* d_b, int w, int h_img, int pitch,
                          float* d_flow) {

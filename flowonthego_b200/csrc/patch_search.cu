@@ -38,6 +38,11 @@ __host__ __device__ constexpr int gcd_ce(int a, int b) { return b == 0 ? a : gcd
 // Shared-memory window of the target image per patch: every position the search may sample lies
 // within outlierthresh = p/2 of the start position (else the patch is reset to its start), so a
 // (2p+4)^2 window anchored at floor(start) - p - 1 covers all bilinear taps of all iterations.
+#ifndef DIS_PS_THREADS
+#define DIS_PS_THREADS 128
+#endif
+constexpr int kPsThreads = DIS_PS_THREADS;  // threads per CTA: 8 per patch
+
 template <int P>
 struct Win {
   // width: covers 2p+3 columns, and W - P is a multiple of 8 so that the two row segments an octet
@@ -52,7 +57,7 @@ struct Win {
 // from global memory (L1/L2) instead of a staged window, and for p > 8 the template and gradients are
 // re-read per iteration instead of being held in registers.
 template <int P, bool L2, int NC>
-__global__ void __launch_bounds__(128) k_patch_search(const PatchSearchArgs a) {
+__global__ void __launch_bounds__(kPsThreads) k_patch_search(const PatchSearchArgs a) {
   constexpr int N = P * P * NC;
   constexpr int PW = P * NC;            // floats per patch row
   constexpr int NI = N / 8;             // chain length
@@ -334,7 +339,7 @@ __global__ void __launch_bounds__(128) k_patch_search(const PatchSearchArgs a) {
 
 template <int P>
 int launch_p(const PatchSearchArgs& a, cudaStream_t st) {
-  const int threads = 128;
+  const int threads = kPsThreads;
   const int blocks = (a.g.nop * 8 + threads - 1) / threads;
   const size_t smem = (size_t)(threads / 8) * Win<P>::SIZE * sizeof(float);
   if (a.o.noc == 3) {
@@ -351,7 +356,7 @@ int launch_p(const PatchSearchArgs& a, cudaStream_t st) {
 
 template <int P>
 void init_p() {
-  const int smem = (int)((128 / 8) * Win<P>::SIZE * sizeof(float));
+  const int smem = (int)((kPsThreads / 8) * Win<P>::SIZE * sizeof(float));
   cudaFuncSetAttribute(k_patch_search<P, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaFuncSetAttribute(k_patch_search<P, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }

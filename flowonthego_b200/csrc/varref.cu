@@ -381,11 +381,16 @@ struct SorArgs {
   int* prog;                    // [0] epoch, [1] ticket, [2 + t*K + k] pacing hint: completed steps of item (t,k)
 };
 
-constexpr int kCH = 16;       // steps per TMA chunk of the coefficient streams
-constexpr int kNS = 2;        // TMA stages in flight
-constexpr int kRD = 32;       // record ring slots (power of two >= 2 groups + 2)
-constexpr int kG = 16;        // steps per group: prefetch / validation / pacing-hint granularity
-constexpr size_t kSorSmem = (size_t)kNS * kCH * 32 * 16 * 2 + (size_t)kRD * 32 * 16 + 3 * kRD * 16 + kNS * 8;
+// kG = steps per group: prefetch / validation / pacing-hint granularity, = steps per TMA chunk of the coefficient
+// streams (kCH); the record ring holds the group being consumed and the prefetched one (kRD = 2 kG).
+// Two instantiations: kG = 16 has the lowest latency for a lone pair (fewest per-group overheads; 49.5 KB of shared
+// memory per warp), kG = 8 is ~10 % slower alone but holds 24.9 KB, which is worth +5.6 % pairs/s when many pairs
+// share the GPU.
+constexpr int kNS = 2;  // TMA stages in flight
+template <int kG>
+constexpr size_t sor_smem() {
+  return (size_t)kNS * kG * 32 * 16 * 2 + (size_t)(2 * kG) * 32 * 16 + 3 * (2 * kG) * 16 + kNS * 8;
+}
 
 __device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -425,7 +430,9 @@ __device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
       : "memory");
 }
 
+template <int kG>
 __global__ void __launch_bounds__(32) k_sor_wavefront(const SorArgs a) {
+  constexpr int kCH = kG, kRD = 2 * kG;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* const sA = smem_raw;                                          // [kNS*kCH][32] float4
   unsigned char* const sB = smem_raw + (size_t)kNS * kCH * 512;                // [kNS*kCH][32] float4
@@ -703,7 +710,10 @@ __global__ void __launch_bounds__(256) k_update(int w, int h, float2* __restrict
 }  // namespace
 
 // per-device opt-in to > 48 KB dynamic shared memory (called from dis_create on the handle's device)
-void varref_init_device() { cudaFuncSetAttribute(k_sor_wavefront, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSorSmem); }
+void varref_init_device() {
+  cudaFuncSetAttribute(k_sor_wavefront<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sor_smem<16>());
+  cudaFuncSetAttribute(k_sor_wavefront<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sor_smem<8>());
+}
 
 void varref_sizes(int w, int h, int n_solver, size_t* n_coef4, size_t* n_du4, size_t* n_prog) {
   const Skew sk(w, h);
@@ -752,7 +762,10 @@ int launch_varref(const LevelGeom& g, const VarParams& v, const float* I0, const
     {
       // each sweep reads 9 arrays and writes 2: 44 B/px
       ProfScope ps(prof, "k_sor_wavefront", g.lv, 44.0 * T * n);
-      k_sor_wavefront<<<T * K, 32, kSorSmem, st>>>(sa);
+      if (v.sor_group == 16)
+        k_sor_wavefront<16><<<T * K, 32, sor_smem<16>(), st>>>(sa);
+      else
+        k_sor_wavefront<8><<<T * K, 32, sor_smem<8>(), st>>>(sa);
     }
     launches += 2;
   }

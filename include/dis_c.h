@@ -102,6 +102,13 @@ int dis_create_c(const dis_params* params, int channels, int max_w, int max_h, i
 int dis_destroy(dis_handle* h);
 /* Replaces the parameter set (workspace is re-planned; fails if it no longer fits). */
 int dis_set_params(dis_handle* h, const dis_params* params);
+/* Execution options; none of them changes results.
+ *   DIS_OPT_SOR_GROUP  8: smaller shared-memory footprint of the SOR wavefront kernel, best pairs/s when many
+ *                      handles share the GPU; 16: lowest latency for a lone pair (about 7 % at 1080p); 0 (default):
+ *                      16 when the finest processed level has >= 2^20 pixels (it fills the GPU alone), else 8.
+ *   DIS_OPT_USE_GRAPH  1 (default): record a run into a CUDA graph and replay it; 0: launch kernel by kernel. */
+typedef enum dis_option { DIS_OPT_SOR_GROUP = 1, DIS_OPT_USE_GRAPH = 2 } dis_option;
+int dis_set_option(dis_handle* h, int option, int value);
 /* Last error text of this handle (or of dis_create when h is NULL). Never NULL. */
 const char* dis_last_error(const dis_handle* h);
 
@@ -166,6 +173,21 @@ int dis_read_flo(const char* path, float* flow_uv, size_t n_floats, int* w, int*
 int dis_read_image_gray(const char* path, uint8_t* out, size_t cap, int* w, int* h);
 /* Colour build (kroeger/run_dense.cpp:203-206 cv::imread(.., COLOR)): interleaved BGR, 3*w*h bytes. */
 int dis_read_image_bgr(const char* path, uint8_t* out, size_t cap, int* w, int* h);
+
+/* ---- groups: several pairs per launch ----------------------------------------------------------------- */
+/* A group owns n engine handles and records their runs as n parallel branches of one CUDA graph, launched on one
+ * stream: the device runs n times as many dependent kernel chains per hardware work queue.  Each
+ * pair's result is bit-identical to dis_run_u8.  d_a / d_b / d_flow: arrays of n_pairs device pointers
+ * (n_pairs <= n); all pairs share w, h and pitch.  Asynchronous; dis_group_wait() waits for all pairs. */
+typedef struct dis_group dis_group;
+int dis_group_create(const dis_params* params, int channels, int max_w, int max_h, int device, int n, dis_group** out);
+void dis_group_destroy(dis_group* g);
+int dis_group_size(const dis_group* g);
+int dis_group_submit_u8_device(dis_group* g, int n_pairs, const uint8_t* const* d_a, const uint8_t* const* d_b, int w,
+                               int h_img, int pitch, float* const* d_flow);
+int dis_group_wait(dis_group* g);
+void* dis_group_stream(dis_group* g);
+const char* dis_group_last_error(const dis_group* g);
 
 /* ---- video-stream front end ------------------------------------------------------------------ */
 /* Consecutive frames in, one flow field per consecutive pair out (the loop the reference's CUDA twin runs over a

@@ -231,6 +231,46 @@ def test_engine_reuse_across_sizes_and_params():
         F.Engine(params(2, 64, lv_f=6, lv_l=3), 64, 48)  # coarsest level would be 1x1
 
 
+def test_execution_options_do_not_change_results():
+    """DIS_OPT_SOR_GROUP (8 | 16) and DIS_OPT_USE_GRAPH only change how the work is scheduled."""
+    a, b, _ = synth_pair(500, 300, seed=21)
+    p = params(3, 512, lv_f=3, lv_l=0)
+    ref = port.run_u8(a, b, p.to_dict())
+    with F.Engine(p, 500, 300) as e:
+        for grp in (8, 16):
+            for graph in (1, 0):
+                e.set_option(api.OPT_SOR_GROUP, grp)
+                e.set_option(api.OPT_USE_GRAPH, graph)
+                assert bits_differ(e.run_u8(a, b), ref) == 0, (grp, graph)
+                assert bits_differ(e.run_u8(a, b), ref) == 0, (grp, graph)  # replay
+        with pytest.raises(F.DisError):
+            e.set_option(api.OPT_SOR_GROUP, 12)
+
+
+def test_group_of_pairs_per_launch():
+    """dis_group_*: n pairs as parallel branches of one graph; every pair equals a separate run."""
+    import torch
+    w, h, n = 322, 198, 3
+    p = params(2, 1024, lv_f=3, lv_l=1)
+    pairs = [synth_pair(w, h, seed=30 + k)[:2] for k in range(n)]
+    da = [torch.from_numpy(x[0]).cuda() for x in pairs]
+    db = [torch.from_numpy(x[1]).cuda() for x in pairs]
+    out = torch.zeros((n, h, w, 2), dtype=torch.float32, device="cuda")
+    with F.EngineGroup(p, w, h, n) as g:
+        for rep in range(2):  # capture, then replay
+            out.zero_()
+            g.submit_u8_device([x.data_ptr() for x in da], [x.data_ptr() for x in db], w, h, w,
+                               [out[k].data_ptr() for k in range(n)])
+            g.wait()
+            for k in range(n):
+                assert bits_differ(out[k].cpu().numpy(), port.run_u8(pairs[k][0], pairs[k][1], p.to_dict())) == 0, (rep, k)
+        g.submit_u8_device([da[0].data_ptr()], [db[0].data_ptr()], w, h, w, [out[2].data_ptr()])  # fewer pairs
+        g.wait()
+        assert bits_differ(out[2].cpu().numpy(), out[0].cpu().numpy()) == 0
+        with pytest.raises(F.DisError):
+            g.submit_u8_device([0], [0], w, h, w, [0])
+
+
 def test_async_and_device_entry_points():
     import torch
     a, b, _ = synth_pair(320, 240, seed=4)
