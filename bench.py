@@ -141,7 +141,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._pump, daemon=True)
             self.th.start()
@@ -181,7 +181,7 @@ class ClockSampler:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=24)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=128, help="frame pairs per step per GPU")
@@ -381,7 +381,13 @@ def main():
         pair_bytes = alg_bytes(W1080, H1080, 12, 0.75, 6, 2, True)
         tot_ms = sum(k["ms"] for k in per_kernel.values())
         # ncu --set full captures (profiles/): dram bytes read+write per launch of the dominant kernels
-        traffic = {"k_sor_wavefront": None, "k_patch_search": None}
+        traffic = {}
+        try:  # dram bytes per launch from the committed ncu pass of the same pair (profiles/r01_traffic_c3.json)
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic_c3.json")))["per_pair"]
+            for kname, r in prof.items():
+                traffic[kname.split("<")[0]] = (r["dram_read_MB"] + r["dram_write_MB"]) * 1e6 / r["launches"]
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": top[0], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic.get(top[0]), "peak_source": peak_src,
                 "note": "k_sor_wavefront keeps the reference's lexicographic Gauss-Seidel order, so it is bound by the "
