@@ -27,6 +27,7 @@ struct LevelGeom {
 struct OptParams {
   int p, novals, steps, max_iter, min_iter, patnorm, costfct, noc;
   float outlierthresh, dp_thresh, dr_thresh, res_thresh;
+  float outlier_sq;  // largest x with sqrtf(x) <= outlierthresh: sqrtf(x) > thresh  <=>  x > outlier_sq, exactly
 };
 
 struct VarParams {  // kroeger/refine_variational.cpp:28-42

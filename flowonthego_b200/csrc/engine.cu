@@ -175,6 +175,13 @@ void derive_opt(const dis_params& q, int noc, OptParams* o) {
   o->noc = noc;
   o->p = q.patchsz;
   o->outlierthresh = (float)o->p / 2;
+  {  // IEEE sqrtf is monotonic, so the reference's `norm() > outlierthresh` (patch.cpp:196) is a threshold on the
+     // squared norm; find it with the host's correctly rounded sqrtf
+    float x = o->outlierthresh * o->outlierthresh;
+    while (sqrtf(nextafterf(x, INFINITY)) <= o->outlierthresh) x = nextafterf(x, INFINITY);
+    while (sqrtf(x) > o->outlierthresh) x = nextafterf(x, 0.0f);
+    o->outlier_sq = x;
+  }
   o->max_iter = q.maxiter;
   o->min_iter = q.miniter;
   o->dp_thresh = q.mindprate * q.mindprate;

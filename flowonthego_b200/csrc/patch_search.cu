@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(kPsThreads) k_patch_search(const PatchSearchAr
         ptx = (float)cx + px;
         pty = (float)cy + py;
         const float ox = stx - ptx, oy = sty - pty;
-        if (sqrtf(ox * ox + oy * oy) > a.o.outlierthresh || ptx < a.g.lb || pty < a.g.lb ||
+        if (ox * ox + oy * oy > a.o.outlier_sq || ptx < a.g.lb || pty < a.g.lb ||  // sqrtf(.) > outlierthresh
             ptx > a.g.ubw || pty > a.g.ubh) {
           px = pinx;
           py = piny;
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(kPsThreads) k_patch_search(const PatchSearchAr
             d = copysignf(sqrtf((sqrtf(1.0f + (d * d) / 25.0f) - 1.0f) * 50.0f), d);
         }
         const float ad = fabsf(d);
-        R[i] = ad;
+        R[i] = d;  // |d| is taken when the weights are written out
         const float tx = (REG ? GX[i] : __ldg(a.I0x + base + eoff(i))) * d;
         const float ty = (REG ? GY[i] : __ldg(a.I0y + base + eoff(i))) * d;
         if (i == 0) {
@@ -317,10 +317,10 @@ __global__ void __launch_bounds__(kPsThreads) k_patch_search(const PatchSearchAr
         if (!conv) {
           const float mares_old = mares;
           mares = asum / (float)N;
-          if (!((cnt < a.o.max_iter) & (mares > a.o.res_thresh) &
-                ((cnt < a.o.min_iter) | (dp_sq / dp_sq_init >= a.o.dp_thresh)) &
-                ((cnt < a.o.min_iter) | (mares / mares_old <= a.o.dr_thresh))))
-            conv = true;
+          bool go = (cnt < a.o.max_iter) & (mares > a.o.res_thresh);
+          if (cnt >= a.o.min_iter)  // the two rate tests (and their divisions) only once min_iter is reached
+            go = go & (dp_sq / dp_sq_init >= a.o.dp_thresh) & (mares / mares_old <= a.o.dr_thresh);
+          if (!go) conv = true;
         }
       }
     }
@@ -332,8 +332,8 @@ __global__ void __launch_bounds__(kPsThreads) k_patch_search(const PatchSearchAr
     if (c == 0) a.pflow[ip] = make_float2(px, py);
     float* pw = a.pweight + (size_t)ip * N;
 #pragma unroll
-    for (int i = 0; i < NI; ++i) pw[8 * i + c] = oob_start ? 0.0f : R[i];
-    if (EX && c < 4) pw[8 * NI + c] = oob_start ? 0.0f : R[NE - 1];
+    for (int i = 0; i < NI; ++i) pw[8 * i + c] = oob_start ? 0.0f : fabsf(R[i]);
+    if (EX && c < 4) pw[8 * NI + c] = oob_start ? 0.0f : fabsf(R[NE - 1]);
   }
 }
 

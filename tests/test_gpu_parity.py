@@ -388,3 +388,15 @@ def test_rgb_cli(tmp_path, golden_dir):
     pd = ref_driver.parse_params(argv)
     assert bits_differ(F.read_flo(out), port.run_u8(A, B, pd)) == 0
     assert bits_differ(F.run_dense(names[0], names[1], None, *argv, channels=3), port.run_u8(A, B, pd)) == 0
+
+
+def test_rgb_full_size_1080p():
+    """Colour at the benchmark size: 1920x1080 BGR pair, preset 3 + variational, against the oracle."""
+    a, b, gt = synth_pair_bgr(1920, 1080, seed=4)
+    p = params(3, 1920)
+    with F.Engine(p, 1920, 1080, channels=3) as e:
+        flow = e.run_u8(a, b)
+        assert bits_differ(flow, e.run_u8(a, b)) == 0
+    assert_flow_parity(flow, port.run_u8(a, b, p.to_dict()), 12, 2)
+    epe = np.sqrt(((flow - gt) ** 2).sum(-1))[48:-48, 48:-48]
+    assert epe.mean() < 0.5, epe.mean()
