@@ -63,10 +63,98 @@ __global__ void __launch_bounds__(256) k_finish(const float2* __restrict__ fl, i
   }
 }
 
+// Scale 4 (lv_l = 2, the 1080p operating points) with padding offsets that are multiples of 4: an aligned 4x4
+// block of output pixels reads a 3x3 neighbourhood of the level flow; the four horizontal lerps of each source row
+// are shared by the output rows that use it.  Every value is produced by the same expression as in k_finish
+// (horizontal lerp of the pre-scaled samples, then vertical lerp), so the result is bit-identical.  Blocks that
+// touch the border clamps or the crop edge fall back to the per-pixel form.
+__global__ void __launch_bounds__(256) k_finish_x4(const float2* __restrict__ fl, int wl, int hl, int left, int top,
+                                                   int w_org, int h_org, const Mailbox* __restrict__ mb) {
+  float2* __restrict__ out = mb->out;
+  const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y * blockDim.y + threadIdx.y;
+  const int x0 = bx * 4, y0 = by * 4;
+  if (x0 >= w_org || y0 >= h_org) return;
+  const int X0 = x0 + left, Y0 = y0 + top;  // multiples of 4
+  const int cx = X0 >> 2, cy = Y0 >> 2;
+  const float s = 4.0f, inv = 0.25f;
+  const bool interior = cx >= 1 && cx + 1 <= wl - 2 && cy >= 1 && cy + 1 <= hl - 2 && x0 + 3 < w_org && y0 + 3 < h_org;
+  if (interior) {
+    float fx[4], fy[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {  // sx = cx-1, cx-1, cx, cx for k = 0..3 (same for rows)
+      const float px = ((float)(X0 + k) + 0.5f) * inv - 0.5f, py = ((float)(Y0 + k) + 0.5f) * inv - 0.5f;
+      fx[k] = px - (float)(cx - 1 + (k >> 1));
+      fy[k] = py - (float)(cy - 1 + (k >> 1));
+    }
+    float2 H[3][4];  // horizontally interpolated, per source row
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const float2* row = fl + (size_t)(cy - 1 + r) * wl + (cx - 1);
+      const float2 p0 = __ldg(row), p1 = __ldg(row + 1), p2 = __ldg(row + 2);
+      const float2 q0 = make_float2(p0.x * s, p0.y * s), q1 = make_float2(p1.x * s, p1.y * s),
+                   q2 = make_float2(p2.x * s, p2.y * s);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 a = (k >> 1) ? q1 : q0, b = (k >> 1) ? q2 : q1;
+        H[r][k].x = a.x * (1.f - fx[k]) + b.x * fx[k];
+        H[r][k].y = a.y * (1.f - fx[k]) + b.y * fx[k];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = j >> 1;
+      float2 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        v[k].x = H[r][k].x * (1.f - fy[j]) + H[r + 1][k].x * fy[j];
+        v[k].y = H[r][k].y * (1.f - fy[j]) + H[r + 1][k].y * fy[j];
+      }
+      float2* o = out + (size_t)(y0 + j) * w_org + x0;
+      if (((size_t)o & 15) == 0) {
+        reinterpret_cast<float4*>(o)[0] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+        reinterpret_cast<float4*>(o)[1] = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = v[k];
+      }
+    }
+    return;
+  }
+  // border block: per-pixel form with the clamps of cv::resize
+  for (int j = 0; j < 4 && y0 + j < h_org; ++j) {
+    float fyv = ((float)(Y0 + j) + 0.5f) * inv - 0.5f;
+    int sy = (int)floorf(fyv);
+    fyv -= (float)sy;
+    if (sy < 0) { fyv = 0.0f; sy = 0; }
+    if (sy >= hl - 1) { fyv = 0.0f; sy = hl - 1; }
+    const float2* r0 = fl + (size_t)sy * wl;
+    const float2* r1 = fl + (size_t)min(sy + 1, hl - 1) * wl;
+    for (int k = 0; k < 4 && x0 + k < w_org; ++k) {
+      float fxv = ((float)(X0 + k) + 0.5f) * inv - 0.5f;
+      int sx = (int)floorf(fxv);
+      fxv -= (float)sx;
+      if (sx < 0) { fxv = 0.0f; sx = 0; }
+      if (sx >= wl - 1) { fxv = 0.0f; sx = wl - 1; }
+      const int sx1 = min(sx + 1, wl - 1);
+      const float2 p00 = __ldg(r0 + sx), p01 = __ldg(r0 + sx1), p10 = __ldg(r1 + sx), p11 = __ldg(r1 + sx1);
+      const float a0 = (p00.x * s) * (1.f - fxv) + (p01.x * s) * fxv;
+      const float a1 = (p10.x * s) * (1.f - fxv) + (p11.x * s) * fxv;
+      const float b0 = (p00.y * s) * (1.f - fxv) + (p01.y * s) * fxv;
+      const float b1 = (p10.y * s) * (1.f - fxv) + (p11.y * s) * fxv;
+      out[(size_t)(y0 + j) * w_org + x0 + k] = make_float2(a0 * (1.f - fyv) + a1 * fyv, b0 * (1.f - fyv) + b1 * fyv);
+    }
+  }
+}
+
 }  // namespace
 
 void launch_finish(const float2* flow_l, int wl, int hl, int lv_l, int left, int top, int w_org, int h_org,
                    const Mailbox* mb, cudaStream_t st) {
+  if (lv_l == 2 && (left & 3) == 0 && (top & 3) == 0) {
+    dim3 block(32, 8), grid((w_org + 127) / 128, (h_org + 31) / 32);
+    k_finish_x4<<<grid, block, 0, st>>>(flow_l, wl, hl, left, top, w_org, h_org, mb);
+    return;
+  }
   dim3 block(32, 8), grid((w_org + 127) / 128, (h_org + 7) / 8);
   k_finish<<<grid, block, 0, st>>>(flow_l, wl, hl, lv_l, left, top, w_org, h_org, mb);
 }
