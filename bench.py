@@ -411,7 +411,7 @@ def main():
             from tests.synth import synth_pair
             a4, b4, _ = synth_pair(3840, 2160, seed=2)
             p4 = F.Params.from_argv("7 0 16 16 0.05 0.95 0 12 0.75 0 1 0 1 10 10 5 1 3 1.6 0".split())
-            S4 = 4
+            S4 = 16  # saturates at 4K (tools/streams_sweep_4k.py: 4 -> 6.7, 8 -> 6.1, 16 -> 5.9, 32 -> 5.9 ms/pair)
             eng4 = [F.Engine(p4, 3840, 2160, local_rank) for _ in range(S4)]
             da, db = torch.from_numpy(a4).to(dev), torch.from_numpy(b4).to(dev)
             o4 = torch.empty((S4, 2160, 3840, 2), dtype=torch.float32, device=dev)
@@ -431,11 +431,11 @@ def main():
             eng4[0].submit_u8_device(da.data_ptr(), db.data_ptr(), 3840, 2160, 3840, o4[0].data_ptr())
             eng4[0].wait()
             t0 = time.perf_counter()
-            for i in range(6 * S4):
+            for i in range(4 * S4):
                 eng4[i % S4].submit_u8_device(da.data_ptr(), db.data_ptr(), 3840, 2160, 3840, o4[i % S4].data_ptr())
             for e in eng4:
                 e.wait()
-            thr = (time.perf_counter() - t0) / (6 * S4) * 1e3
+            thr = (time.perf_counter() - t0) / (4 * S4) * 1e3
             b4k = alg_bytes(3840, 2160, 12, 0.75, 7, 0, True)
             extra = {"workload": "C4a: 3840x2160 synthetic pair, p12 ov0.75 lv7->0 16it + variational",
                      "latency_ms_per_pair_1stream": lat, "ms_per_pair_%dstreams" % S4: thr,
