@@ -310,6 +310,38 @@ def main():
     ms_e = timed(lambda: step_host(), Ke)
     e2e_value = N * B * Ke / (ms_e / 1e3)
 
+    # ---- side measurement: host buffers in, the ENGINE's output out (DIS_OPT_LEVEL_OUTPUT: level-lv_l flow as the
+    # OFC::OFClass constructor delivers it; the x4 resize + crop of run_dense.cpp:407-414 is left to the caller)
+    level_extra = None
+    if not args.no_extra:
+        try:
+            from flowonthego_b200 import api as _api
+            wp_, hp_, _, _ = F.padded_size(W1080, H1080, p.lv_f)
+            lshape = (hp_ >> p.lv_l, wp_ >> p.lv_l, 2)
+            h_lvl = [F.pinned_empty(lshape, np.float32) for _ in range(S)]
+            for e in engines:
+                e.set_option(_api.OPT_LEVEL_OUTPUT, 1)
+
+            def step_host_level():
+                for i in range(B):
+                    e = engines[i % S]
+                    if i >= S:
+                        e.wait()
+                    e.submit_u8(h_frames[i], h_frames[i + 1], h_lvl[i % S])
+                for e in engines:
+                    e.wait()
+
+            step_host_level()
+            ms_l = timed(step_host_level, Ke)
+            for e in engines:
+                e.set_option(_api.OPT_LEVEL_OUTPUT, 0)
+            level_extra = {"value": N * B * Ke / (ms_l / 1e3), "unit": UNIT, "h2d_bytes_per_step": 2 * W1080 * H1080 * B,
+                           "d2h_bytes_per_step": int(np.prod(lshape)) * 4 * B,
+                           "what": "dis_submit_u8 with DIS_OPT_LEVEL_OUTPUT=1: u8 frames in, level-%d flow %dx%d out "
+                                   "(the OFClass output); device-timed like e2e" % (p.lv_l, lshape[1], lshape[0])}
+        except Exception as ex:
+            level_extra = {"error": repr(ex)}
+
     # ---- side measurement: the same host-buffer workload through the video front end (dis_video_*: every frame
     # uploaded once, pairs pipelined over S handles)
     stream_extra = None
@@ -465,6 +497,8 @@ def main():
             line["extra_c4a_4k"] = extra
         if stream_extra is not None:
             line["extra_video_stream_e2e"] = stream_extra
+        if level_extra is not None:
+            line["extra_e2e_engine_output"] = level_extra
         print(json.dumps(line))
     for e in engines:
         e.close()

@@ -183,7 +183,7 @@ def pinned_empty(shape, dtype):
 _PINNED = {}
 
 
-OPT_SOR_GROUP, OPT_USE_GRAPH = 1, 2
+OPT_SOR_GROUP, OPT_USE_GRAPH, OPT_LEVEL_OUTPUT = 1, 2, 3
 
 
 class Engine:
@@ -223,6 +223,8 @@ class Engine:
     def set_option(self, option, value):
         """OPT_SOR_GROUP (8 | 16), OPT_USE_GRAPH (0 | 1); results never change."""
         _check(lib().dis_set_option(self._h, int(option), int(value)), self._h)
+        if int(option) == OPT_LEVEL_OUTPUT:
+            self._level_output = bool(value)
 
     # ---- whole run_dense data path ----------------------------------------------------------
     def run_u8(self, a, b, out=None):
@@ -244,8 +246,15 @@ class Engine:
             raise ValueError("need two %s u8 images of identical shape and pitch" %
                              ("BGR (h, w, 3)" if self.channels == 3 else "grey (h, w)"))
         h, w = a.shape[:2]
+        if getattr(self, "_level_output", False):  # OPT_LEVEL_OUTPUT: raw engine output at level lv_l
+            wp, hp, _, _ = padded_size(w, h, self.params.lv_f)
+            shape = (hp >> self.params.lv_l, wp >> self.params.lv_l, 2)
+        else:
+            shape = (h, w, 2)
         if out is None:
-            out = np.empty((h, w, 2), np.float32)
+            out = np.empty(shape, np.float32)
+        elif out.shape != shape:
+            raise ValueError("flow buffer %s, expected %s" % (out.shape, shape))
         self._keep = (a, b, out)
         _check(lib().dis_submit_u8(self._h, a.ctypes.data, b.ctypes.data, w, h, a.strides[0], _as_fp(out)), self._h)
 

@@ -115,6 +115,7 @@ struct dis_handle {
   // graph
   bool use_graph = true;
   int sor_group = 0;  // DIS_OPT_SOR_GROUP: 0 auto, 8, 16
+  bool level_output = false;  // DIS_OPT_LEVEL_OUTPUT
   cudaGraphExec_t graph_exec = nullptr;
   int graph_w = 0, graph_h = 0;
 
@@ -764,6 +765,9 @@ int dis_set_option(dis_handle* h, int option, int value) {
         h->sor_group = value;
       }
       return DIS_OK;
+    case DIS_OPT_LEVEL_OUTPUT:
+      h->level_output = value != 0;
+      return DIS_OK;
     case DIS_OPT_USE_GRAPH:
       h->use_graph = value != 0;
       return DIS_OK;
@@ -1013,7 +1017,12 @@ int dis_submit_u8(dis_handle* h, const uint8_t* a, const uint8_t* b, int w, int 
   rc = enqueue_run_device(h, h->d_a, h->d_b, (int)rowb, h->d_out);
   if (rc != DIS_OK) return rc;
   CU(h, cudaEventRecord(h->ev[2], h->stream));
-  CU(h, cudaMemcpyAsync(flow_out, h->d_out, sizeof(float2) * (size_t)w * h_img, cudaMemcpyDeviceToHost, h->stream));
+  if (h->level_output) {  // the engine's own output (OFClass outflow): level lv_l, padded size
+    const LevelBufs& L = h->lv[h->P.lv_l];
+    CU(h, cudaMemcpyAsync(flow_out, L.flow, sizeof(float2) * (size_t)L.g.w * L.g.h, cudaMemcpyDeviceToHost, h->stream));
+  } else {
+    CU(h, cudaMemcpyAsync(flow_out, h->d_out, sizeof(float2) * (size_t)w * h_img, cudaMemcpyDeviceToHost, h->stream));
+  }
   CU(h, cudaEventRecord(h->ev[3], h->stream));
   h->in_flight = true;
   return DIS_OK;

@@ -106,8 +106,12 @@ int dis_set_params(dis_handle* h, const dis_params* params);
  *   DIS_OPT_SOR_GROUP  8: smaller shared-memory footprint of the SOR wavefront kernel, best pairs/s when many
  *                      handles share the GPU; 16: lowest latency for a lone pair (about 7 % at 1080p); 0 (default):
  *                      16 when the finest processed level has >= 2^20 pixels (it fills the GPU alone), else 8.
- *   DIS_OPT_USE_GRAPH  1 (default): record a run into a CUDA graph and replay it; 0: launch kernel by kernel. */
-typedef enum dis_option { DIS_OPT_SOR_GROUP = 1, DIS_OPT_USE_GRAPH = 2 } dis_option;
+ *   DIS_OPT_USE_GRAPH  1 (default): record a run into a CUDA graph and replay it; 0: launch kernel by kernel.
+ * DIS_OPT_LEVEL_OUTPUT changes WHAT dis_run_u8 / dis_submit_u8 copy back, not how it is computed: 1 = the engine's
+ * own output as the OFC::OFClass constructor delivers it (level lv_l, (w_pad/2^lv_l) x (h_pad/2^lv_l) x 2 floats,
+ * see dis_padded_size), leaving the x2^lv_l resize and crop of kroeger/run_dense.cpp:407-414 to the caller -- 16x
+ * less device-to-host traffic at lv_l = 2; 0 (default) = full-resolution flow. */
+typedef enum dis_option { DIS_OPT_SOR_GROUP = 1, DIS_OPT_USE_GRAPH = 2, DIS_OPT_LEVEL_OUTPUT = 3 } dis_option;
 int dis_set_option(dis_handle* h, int option, int value);
 /* Last error text of this handle (or of dis_create when h is NULL). Never NULL. */
 const char* dis_last_error(const dis_handle* h);

@@ -245,6 +245,20 @@ def test_execution_options_do_not_change_results():
                 assert bits_differ(e.run_u8(a, b), ref) == 0, (grp, graph)  # replay
         with pytest.raises(F.DisError):
             e.set_option(api.OPT_SOR_GROUP, 12)
+        # OPT_LEVEL_OUTPUT: the OFClass-style output; the caller's resize + crop (here: the oracle's) gives the same flow
+        e.set_option(api.OPT_LEVEL_OUTPUT, 1)
+        lvl = e.run_u8(a, b)
+        wp, hp, left, top = F.padded_size(500, 300, 3)
+        assert lvl.shape == (hp, wp, 2)
+        assert bits_differ(port.finish(lvl, 0, left, top, 500, 300), ref) == 0
+    p1 = params(2, 1024, lv_f=3, lv_l=1)
+    with F.Engine(p1, 500, 300) as e:
+        full = e.run_u8(a, b)
+        e.set_option(api.OPT_LEVEL_OUTPUT, 1)
+        lvl = e.run_u8(a, b)
+        assert lvl.shape == (hp >> 1, wp >> 1, 2)
+        assert bits_differ(lvl, e.level_flow(500, 300)) == 0
+        assert bits_differ(port.finish(lvl, 1, left, top, 500, 300), full) == 0
 
 
 def test_group_of_pairs_per_launch():
