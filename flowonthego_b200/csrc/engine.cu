@@ -498,7 +498,9 @@ int enqueue_engine(dis_handle* h, const float2* d_initflow) {
       StageClock ck(h, &h->tm.varref_ms);
       vp.n_inner = q.tv_innerit * (sl + 1);  // refine_variational.cpp:36
       int n = launch_varref(L.g, vp, L.Ia, L.Ib, L.flow, h->vb, h->stream, prof);
-      if (n < 0) return fail(h, DIS_ERR_UNSUPPORTED, "level %d (%dx%d) too small for refinement", sl, L.g.w, L.g.h);
+      if (n < 0)
+        return fail(h, DIS_ERR_UNSUPPORTED, "refinement of level %d (%dx%d, %d sweeps): need width >= 2, height >= 4, 1..256 sweeps",
+                    sl, L.g.w, L.g.h, vp.n_solver);
       h->launches += n;
       if (fb && sl > q.lv_l) {  // oflow.cpp:291-294
         n = launch_varref(L.g, vp, L.Ib, L.Ia, L.flow_bw, h->vb, h->stream, prof);
@@ -667,7 +669,7 @@ int dis_params_validate(const dis_params* p, char* why, size_t why_len) {
   else if (!(p->poverl >= 0.0f && p->poverl < 1.0f)) msg = "poverl must be in [0,1)";
   else if (p->costfct < 0 || p->costfct > 2) msg = "costfct must be 0 (L2), 1 (L1) or 2 (Huber)";
   else if (p->maxiter < 0 || p->miniter < 0) msg = "negative iteration count";
-  else if (p->usetvref && p->tv_solverit < 1) msg = "tv_solverit must be >= 1";
+  else if (p->usetvref && (p->tv_solverit < 1 || p->tv_solverit > 256)) msg = "tv_solverit must be in 1..256";
   else if (p->usetvref && p->tv_innerit < 0) msg = "tv_innerit must be >= 0";
   if (msg) {
     if (why && why_len) snprintf(why, why_len, "%s", msg);

@@ -472,7 +472,9 @@ __global__ void __launch_bounds__(32) k_sor_wavefront(const SorArgs a) {
   const bool no_up = (j == 0), no_dn = (j >= h - 1);
   const bool edge_blk = (k == 0) || (k == K - 1);
   const int epoch = ld_volatile(a.prog);
-  const int tag_cur = (epoch << 5) | t, tag_prev = (epoch << 5) | (t - 1);  // epoch >= 1, T <= 32
+  // epoch >= 1, T <= 256 (dis_params_validate); unsigned arithmetic: the epoch may wrap, tags only have to differ
+  // from those of the launches that last wrote the same records
+  const int tag_cur = (int)(((unsigned)epoch << 8) | (unsigned)t), tag_prev = (int)(((unsigned)epoch << 8) | (unsigned)(t - 1));
   const bool chk_old = (t > 0);                           // my old records carry the previous sweep's tag
   const int* p_prev = (t > 0) ? a.prog + 2 + (t - 1) * K + k : nullptr;                // same block, previous sweep
   const int* p_upb = has_up ? a.prog + 2 + t * K + k - 1 : nullptr;                     // block above, same sweep
@@ -726,7 +728,7 @@ void varref_sizes(int w, int h, int n_solver, size_t* n_coef4, size_t* n_du4, si
 int launch_varref(const LevelGeom& g, const VarParams& v, const float* I0, const float* I1, float2* flow,
                   const VarRefBuffers& b, cudaStream_t st, Prof* prof) {
   const int w = g.w, h = g.h, n = w * h;
-  if (w < 2 || h < 4 || v.n_solver < 1 || v.n_solver > 32) return -1;  // reference would take its slow path / read out of range
+  if (w < 2 || h < 4 || v.n_solver < 1 || v.n_solver > 256) return -1;  // reference would take its slow path / read out of range
   int launches = 0;
   dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
   // algorithmic bytes per SURVEY.md section 8(d): warp+mask 28 B/px, derivative stack 40 B/px

@@ -261,6 +261,17 @@ def test_execution_options_do_not_change_results():
         assert bits_differ(port.finish(lvl, 1, left, top, 500, 300), full) == 0
 
 
+def test_many_sor_sweeps_and_inner_iterations():
+    """tv_solverit beyond 32 (the sweep index lives in the record tags) and several inner iterations per level."""
+    a, b, _ = synth_pair(200, 140, seed=8)
+    for kw in (dict(tv_solverit=40, tv_innerit=1), dict(tv_solverit=2, tv_innerit=4, tv_sor=1.2)):
+        p = params(2, 1024, lv_f=2, lv_l=0, **kw)
+        with F.Engine(p, 200, 140) as e:
+            assert bits_differ(e.run_u8(a, b), port.run_u8(a, b, p.to_dict())) == 0, kw
+    with pytest.raises(F.DisError):
+        F.Engine(params(2, 1024, tv_solverit=300), 200, 140)
+
+
 def test_group_of_pairs_per_launch():
     """dis_group_*: n pairs as parallel branches of one graph; every pair equals a separate run."""
     import torch

@@ -53,7 +53,7 @@ def test_validate_rejects_out_of_scope():
     buf = ctypes.create_string_buffer(200)
     ok = F.Params.preset(2, 1024)
     assert L.dis_params_validate(ctypes.byref(ok), buf, 200) == 0
-    for kw in (dict(patchsz=7), dict(patchsz=18), dict(lv_l=6), dict(costfct=10), dict(poverl=1.0), dict(tv_solverit=0)):
+    for kw in (dict(patchsz=7), dict(patchsz=18), dict(lv_l=6), dict(costfct=10), dict(poverl=1.0), dict(tv_solverit=0), dict(tv_solverit=257)):
         bad = ok.copy(**kw)
         assert L.dis_params_validate(ctypes.byref(bad), buf, 200) != 0, kw
         assert len(buf.value) > 0
