@@ -101,6 +101,9 @@ def lib():
         L.dis_auto_first_scale.argtypes = [ip, ip, ip]
         L.dis_create.argtypes = [pp, ip, ip, ip, ctypes.POINTER(vp)]
         L.dis_create_c.argtypes = [pp, ip, ip, ip, ip, ctypes.POINTER(vp)]
+        L.dis_create_batch.argtypes = [pp, ip, ip, ip, ip, ip, ctypes.POINTER(vp)]
+        L.dis_batch_size.argtypes = [vp]
+        L.dis_submit_u8_device_batch.argtypes = [vp, ip, ctypes.POINTER(vp), ctypes.POINTER(vp), ip, ip, ip, ctypes.POINTER(vp)]
         L.dis_destroy.argtypes = [vp]
         L.dis_set_params.argtypes = [vp, pp]
         L.dis_set_option.argtypes = [vp, ip, ip]
@@ -189,14 +192,16 @@ OPT_SOR_GROUP, OPT_USE_GRAPH, OPT_LEVEL_OUTPUT = 1, 2, 3
 class Engine:
     """One engine instance = one dis_handle (stream, workspace, CUDA graph)."""
 
-    def __init__(self, params, max_w, max_h, device=0, channels=1):
+    def __init__(self, params, max_w, max_h, device=0, channels=1, batch=1):
         """channels=1: grey (the reference's run_OF_INT build); channels=3: interleaved BGR
-        (run_OF_RGB, SELECTCHANNEL=3)."""
+        (run_OF_RGB, SELECTCHANNEL=3).  batch > 1: every kernel launch serves that many pairs
+        (dis_create_batch; use submit_u8_device_batch)."""
         self._h = ctypes.c_void_p()
         self.params = params if isinstance(params, Params) else Params.from_dict(params)
         self.channels = int(channels)
-        _check(lib().dis_create_c(ctypes.byref(self.params), self.channels, int(max_w), int(max_h), int(device),
-                                  ctypes.byref(self._h)), None)
+        self.batch = int(batch)
+        _check(lib().dis_create_batch(ctypes.byref(self.params), self.channels, int(max_w), int(max_h), int(device),
+                                      self.batch, ctypes.byref(self._h)), None)
         self._keep = None
 
     def close(self):
@@ -261,6 +266,12 @@ class Engine:
     def submit_u8_device(self, d_a, d_b, w, h, pitch, d_flow):
         """Device pointers (ints) in, device pointer out; asynchronous on the engine's stream."""
         _check(lib().dis_submit_u8_device(self._h, d_a, d_b, w, h, pitch, d_flow), self._h)
+
+    def submit_u8_device_batch(self, d_a, d_b, w, h, pitch, d_flow):
+        """Up to `batch` pairs per call: sequences of device pointers (ints); asynchronous."""
+        k = len(d_a)
+        arr = ctypes.c_void_p * k
+        _check(lib().dis_submit_u8_device_batch(self._h, k, arr(*d_a), arr(*d_b), w, h, pitch, arr(*d_flow)), self._h)
 
     def wait(self):
         _check(lib().dis_wait(self._h), self._h)

@@ -21,7 +21,18 @@ struct LevelGeom {
   int nopw, noph, offw, offh, nop;  // patch grid
   int fpitch;      // pitch (in pixels) of per-level planar/float2 work images (= w)
   int noc;         // channels of the padded images: 1 grey, 3 interleaved BGR (SELECTCHANNEL=3); pitch counts floats
+  // Batched handles (dis_create_batch): nb pairs per launch.  Every device buffer of pair b lives at the same
+  // offset inside its own copy of the workspace, bstride bytes after pair b-1's, so a kernel serves pair b by
+  // adding b * bstride to each pointer it was given (bshift below); the batch index rides on a grid dimension.
+  int nb;          // pairs per launch (>= 1)
+  size_t bstride;  // bytes between the workspaces of consecutive pairs
 };
+
+// pointer of pair b given pair 0's pointer (null stays null)
+template <class T>
+__host__ __device__ __forceinline__ T* bshift(T* p, size_t off) {
+  return p ? reinterpret_cast<T*>(reinterpret_cast<uintptr_t>(p) + off) : nullptr;
+}
 
 // Parameters derived in OFClass::OFClass (kroeger/oflow.cpp:75-108)
 struct OptParams {
@@ -57,6 +68,13 @@ struct Mailbox {
   int pitch;  // row pitch of a and b in bytes
 };
 void launch_set_mailbox(Mailbox* mb, const uint8_t* a, const uint8_t* b, float2* out, int pitch, cudaStream_t st);
+constexpr int kMaxBatch = 8;
+struct MailboxBatch {  // by-value kernel argument: the per-run pointers of up to kMaxBatch pairs
+  const uint8_t* a[kMaxBatch];
+  const uint8_t* b[kMaxBatch];
+  float2* out[kMaxBatch];
+};
+void launch_set_mailboxes(Mailbox* mb0, size_t bstride, int nb, const MailboxBatch& m, int pitch, cudaStream_t st);
 
 // ---- launchers (defined in the .cu files) --------------------------------------------------
 // pyramid.cu
@@ -118,6 +136,6 @@ void launch_flow_epe(const float2* d_a, const float2* d_b, int w, int h, int mar
                      unsigned long long* d_pcnt, cudaStream_t st);
 // finish.cu
 void launch_finish(const float2* flow_l, int wl, int hl, int lv_l, int left, int top, int w_org,
-                   int h_org, const Mailbox* mb, cudaStream_t st);
+                   int h_org, const Mailbox* mb, int nb, size_t bstride, cudaStream_t st);
 
 }  // namespace dis

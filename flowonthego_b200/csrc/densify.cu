@@ -39,10 +39,15 @@ __device__ __forceinline__ float patch_absw(const float* pw, int P, int noc, int
 
 // Per-patch integer anchor ceil(pt_iter + 1e-5) (double arithmetic, patchgrid.cpp:304-305), bilinear
 // weights (:310-315) and the level-wide maximum anchor displacement.
-__global__ void __launch_bounds__(256) k_bw_anchors(const LevelGeom g, const OptParams o, const float2* __restrict__ pflow,
-                                                    int2* __restrict__ anchor, float4* __restrict__ wbil, int* __restrict__ maxdisp) {
+__global__ void __launch_bounds__(256) k_bw_anchors(const LevelGeom g, const OptParams o, const float2* __restrict__ pflow0,
+                                                    int2* __restrict__ anchor0, float4* __restrict__ wbil0, int* __restrict__ maxdisp0) {
   const int ip = blockIdx.x * blockDim.x + threadIdx.x;
   if (ip >= g.nop) return;
+  const size_t boff = (size_t)blockIdx.y * g.bstride;  // blockIdx.y = pair of a batched handle
+  const float2* __restrict__ pflow = bshift(pflow0, boff);
+  int2* __restrict__ anchor = bshift(anchor0, boff);
+  float4* __restrict__ wbil = bshift(wbil0, boff);
+  int* __restrict__ maxdisp = bshift(maxdisp0, boff);
   const int gx = ip / g.noph, gy = ip - gx * g.noph;
   const int cx = gx * o.steps + g.offw, cy = gy * o.steps + g.offh;
   const float2 p = pflow[ip];
@@ -62,6 +67,15 @@ __global__ void __launch_bounds__(256) k_densify(const DensifyArgs a) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= a.g.w || y >= a.g.h) return;
+  const size_t boff = (size_t)blockIdx.z * a.g.bstride;  // blockIdx.z = pair of a batched handle
+  const float2* __restrict__ q_pflow = bshift(a.pflow, boff);
+  const float* __restrict__ q_pweight = bshift(a.pweight, boff);
+  const float2* __restrict__ q_pflow_bw = bshift(a.pflow_bw, boff);
+  const float* __restrict__ q_pweight_bw = bshift(a.pweight_bw, boff);
+  const int2* __restrict__ q_anchor = bshift(a.anchor, boff);
+  const float4* __restrict__ q_wbil = bshift(a.wbil, boff);
+  const int* __restrict__ q_maxdisp = bshift(a.maxdisp, boff);
+  float2* __restrict__ q_flow = bshift(a.flow, boff);
   const int P = a.o.p, N = a.o.novals, steps = a.o.steps, half = P / 2;
   // patches whose footprint [c-half, c+half-1] contains the pixel
   // c = g*steps + off  =>  g in [ceil((x-off-half+1)/steps), floor((x-off+half)/steps)]
@@ -86,8 +100,8 @@ __global__ void __launch_bounds__(256) k_densify(const DensifyArgs a) {
         const bool ok = u < nx && v < ny;
         const int ip = ok ? (gx0 + u) * a.g.noph + gy0 + v : 0;
         const int off = ok ? (ly0 - v * steps) * P + (lx0 - u * steps) : 0;
-        wv[u * C + v] = __ldg(a.pweight + (size_t)ip * N + off);
-        fl[u * C + v] = __ldg(a.pflow + ip);
+        wv[u * C + v] = __ldg(q_pweight + (size_t)ip * N + off);
+        fl[u * C + v] = __ldg(q_pflow + ip);
       }
 #pragma unroll
     for (int u = 0; u < C; ++u)
@@ -114,8 +128,8 @@ __global__ void __launch_bounds__(256) k_densify(const DensifyArgs a) {
         const int ip = gx * a.g.noph + gy;
         const int pcy = gy * steps + a.g.offh;
         const int ly = y - pcy + half;
-        const float2 f = __ldg(a.pflow + ip);
-        const float aw = patch_absw(a.pweight + (size_t)ip * N, P, noc, lx, ly, xlo, xhi, max(0, half - pcy));
+        const float2 f = __ldg(q_pflow + ip);
+        const float aw = patch_absw(q_pweight + (size_t)ip * N, P, noc, lx, ly, xlo, xhi, max(0, half - pcy));
         we += aw;
         fu += f.x * aw;
         fv += f.y * aw;
@@ -124,7 +138,7 @@ __global__ void __launch_bounds__(256) k_densify(const DensifyArgs a) {
   }
   if (FB) {
     const int lb = -half, ub = half - 1, w = a.g.w, h = a.g.h;
-    const int D = *a.maxdisp;
+    const int D = *q_maxdisp;
     // a patch can reach x iff its anchor p0 is in [x-ub, x-lb+1]; |p0 - centre| <= D
     int bx0 = x - ub - D - a.g.offw, bx1 = x - lb + 1 + D - a.g.offw;
     int by0 = y - ub - D - a.g.offh, by1 = y - lb + 1 + D - a.g.offh;
@@ -135,12 +149,12 @@ __global__ void __launch_bounds__(256) k_densify(const DensifyArgs a) {
     for (int gx = bx0; gx <= bx1; ++gx)
       for (int gy = by0; gy <= by1; ++gy) {
         const int ip = gx * a.g.noph + gy;
-        const int2 an = __ldg(a.anchor + ip);
+        const int2 an = __ldg(q_anchor + ip);
         const int dx = x - an.x, dy = y - an.y;
         if (dx < lb - 1 || dx > ub || dy < lb - 1 || dy > ub) continue;
-        const float2 f = __ldg(a.pflow_bw + ip);
-        const float4 wb = __ldg(a.wbil + ip);
-        const float* pw = a.pweight_bw + (size_t)ip * N;
+        const float2 f = __ldg(q_pflow_bw + ip);
+        const float4 wb = __ldg(q_wbil + ip);
+        const float* pw = q_pweight_bw + (size_t)ip * N;
         // source element (ex,ey) of the patch sits at target (XT,YT) and feeds this pixel with weight wk
         // accepted source pixels of this patch (xt,yt in [1,w-2] x [1,h-2]) as a rectangle in patch coordinates
         const int bxlo = max(0, 1 - an.x - lb), bxhi = min(P - 1, w - 2 - an.x - lb), bylo = max(0, 1 - an.y - lb);
@@ -164,17 +178,17 @@ __global__ void __launch_bounds__(256) k_densify(const DensifyArgs a) {
     out.x = fu / we;
     out.y = fv / we;
   }
-  a.flow[(size_t)y * a.g.w + x] = out;
+  q_flow[(size_t)y * a.g.w + x] = out;
 }
 
 }  // namespace
 
 void launch_densify(const DensifyArgs& a, cudaStream_t st) {
   dim3 block(32, 8);
-  dim3 grid((a.g.w + 31) / 32, (a.g.h + 7) / 8);
+  dim3 grid((a.g.w + 31) / 32, (a.g.h + 7) / 8, a.g.nb);
   if (a.pflow_bw != nullptr) {
-    cudaMemsetAsync(a.maxdisp, 0, sizeof(int), st);
-    k_bw_anchors<<<(a.g.nop + 255) / 256, 256, 0, st>>>(a.g, a.o, a.pflow_bw, a.anchor, a.wbil, a.maxdisp);
+    cudaMemset2DAsync(a.maxdisp, a.g.bstride ? a.g.bstride : sizeof(int), 0, sizeof(int), a.g.nb, st);  // one counter per pair
+    k_bw_anchors<<<dim3((a.g.nop + 255) / 256, a.g.nb), 256, 0, st>>>(a.g, a.o, a.pflow_bw, a.anchor, a.wbil, a.maxdisp);
     k_densify<true><<<grid, block, 0, st>>>(a);
   } else {
     k_densify<false><<<grid, block, 0, st>>>(a);

@@ -116,6 +116,8 @@ struct dis_handle {
   bool use_graph = true;
   int sor_group = 0;  // DIS_OPT_SOR_GROUP: 0 auto, 8, 16
   bool level_output = false;  // DIS_OPT_LEVEL_OUTPUT
+  int nb = 1;            // pairs per launch (dis_create_batch)
+  size_t bstride = 0;    // bytes between the workspaces of consecutive pairs of the batch
   cudaGraphExec_t graph_exec = nullptr;
   int graph_w = 0, graph_h = 0;
 
@@ -319,7 +321,8 @@ void drop_graph(dis_handle* h) {
 int plan(dis_handle* h, int w, int h_img) {
   if (w <= 0 || h_img <= 0) return fail(h, DIS_ERR_INVALID_ARG, "non-positive image size %dx%d", w, h_img);
   if (w == h->w_org && h_img == h->h_org && !h->lv.empty()) return DIS_OK;
-  const size_t need = carve(h, w, h_img, nullptr, false);
+  const size_t one = carve(h, w, h_img, nullptr, false);  // workspace of one pair (multiple of 256 bytes)
+  const size_t need = one * (size_t)h->nb;
   if (need > h->slab_bytes) {  // grow the slab (sizes above the create-time maximum re-allocate)
     drop_graph(h);
     if (h->slab) {
@@ -332,7 +335,12 @@ int plan(dis_handle* h, int w, int h_img) {
     h->slab_bytes = need;
   }
   drop_graph(h);
-  carve(h, w, h_img, h->slab, true);
+  carve(h, w, h_img, h->slab, true);  // pointers of pair 0; pair b's are bstride * b bytes further (bshift)
+  h->bstride = h->nb > 1 ? one : 0;
+  for (LevelBufs& L : h->lv) {
+    L.g.nb = h->nb;
+    L.g.bstride = h->bstride;
+  }
   // SOR hand-off tags/epoch start from a clean slate (stale bytes could alias a tag)
   CU(h, cudaMemsetAsync(h->slab, 0, h->slab_bytes, h->stream));
   // coarsest level must be large enough for the kernels (and for the reference itself)
@@ -521,7 +529,8 @@ int enqueue_finish(dis_handle* h) {
   const LevelBufs& L = h->lv[h->P.lv_l];
   ProfScope ps(h->kprof_on ? &h->kprof : nullptr, "k_finish", h->P.lv_l,
                8.0 * (double)L.g.w * L.g.h + 8.0 * (double)h->w_org * h->h_org);
-  launch_finish(L.flow, L.g.w, L.g.h, h->P.lv_l, h->left, h->top, h->w_org, h->h_org, h->mailbox, h->stream);
+  launch_finish(L.flow, L.g.w, L.g.h, h->P.lv_l, h->left, h->top, h->w_org, h->h_org, h->mailbox, h->nb, h->bstride,
+                h->stream);
   h->launches++;
   if (const char* dbg = getenv("DIS_DEBUG_EXTRA_LAUNCHES"))  // experiment: cost of a kernel launch at throughput
     for (int i = 0, n = atoi(dbg); i < n; ++i) launch_set_mailbox(h->mailbox + 1, nullptr, nullptr, nullptr, 0, h->stream);
@@ -530,8 +539,27 @@ int enqueue_finish(dis_handle* h) {
 }
 
 // Enqueue the whole device-side run (stage 1 .. finish); replayed from a CUDA graph when possible.
+int enqueue_run_device_batch(dis_handle* h, int n, const uint8_t* const* d_a, const uint8_t* const* d_b, int pitch,
+                             float2* const* d_out);
+
 int enqueue_run_device(dis_handle* h, const uint8_t* d_a, const uint8_t* d_b, int pitch, float2* d_out) {
-  launch_set_mailbox(h->mailbox, d_a, d_b, d_out, pitch, h->stream);
+  return enqueue_run_device_batch(h, 1, &d_a, &d_b, pitch, &d_out);
+}
+
+// n <= nb pairs; the unused slots of a batched handle recompute pair 0 into their own scratch output
+int enqueue_run_device_batch(dis_handle* h, int n, const uint8_t* const* d_a, const uint8_t* const* d_b, int pitch,
+                             float2* const* d_out) {
+  if (h->nb == 1) {
+    launch_set_mailbox(h->mailbox, d_a[0], d_b[0], d_out[0], pitch, h->stream);
+  } else {
+    MailboxBatch m{};
+    for (int b = 0; b < h->nb; ++b) {
+      m.a[b] = d_a[b < n ? b : 0];
+      m.b[b] = d_b[b < n ? b : 0];
+      m.out[b] = b < n ? d_out[b] : bshift(h->d_out, (size_t)b * h->bstride);
+    }
+    launch_set_mailboxes(h->mailbox, h->bstride, h->nb, m, pitch, h->stream);
+  }
   const bool graphable = h->use_graph && !h->taps && !h->stage_timing && !h->kprof_on;
   if (graphable && h->graph_exec && h->graph_w == h->w_org && h->graph_h == h->h_org) {
     CU(h, cudaGraphLaunch(h->graph_exec, h->stream));
@@ -699,7 +727,12 @@ int dis_create(const dis_params* params, int max_w, int max_h, int device, dis_h
 }
 
 int dis_create_c(const dis_params* params, int channels, int max_w, int max_h, int device, dis_handle** out) {
+  return dis_create_batch(params, channels, max_w, max_h, device, 1, out);
+}
+
+int dis_create_batch(const dis_params* params, int channels, int max_w, int max_h, int device, int batch, dis_handle** out) {
   if (!out) return fail(nullptr, DIS_ERR_INVALID_ARG, "out is null");
+  if (batch < 1 || batch > kMaxBatch) return fail(nullptr, DIS_ERR_INVALID_ARG, "batch must be in 1..%d", kMaxBatch);
   *out = nullptr;
   if (channels != 1 && channels != 3) return fail(nullptr, DIS_ERR_UNSUPPORTED, "channels must be 1 (grey) or 3 (BGR)");
   char why[128];
@@ -722,6 +755,7 @@ int dis_create_c(const dis_params* params, int channels, int max_w, int max_h, i
   h->device = device;
   h->P = *params;
   h->noc = channels;
+  h->nb = batch;
   derive_opt(h->P, h->noc, &h->opt);
   h->max_w = max_w;
   h->max_h = max_h;
@@ -997,6 +1031,23 @@ int dis_submit_u8_device(dis_handle* h, const uint8_t* d_a, const uint8_t* d_b, 
   if (rc != DIS_OK) return rc;
   reset_timings(h);
   rc = enqueue_run_device(h, d_a, d_b, pitch, reinterpret_cast<float2*>(d_flow));
+  h->in_flight = rc == DIS_OK;
+  return rc;
+}
+
+int dis_batch_size(const dis_handle* h) { return h ? h->nb : 0; }
+
+int dis_submit_u8_device_batch(dis_handle* h, int n_pairs, const uint8_t* const* d_a, const uint8_t* const* d_b, int w,
+                               int h_img, int pitch, float* const* d_flow) {
+  if (!h || !d_a || !d_b || !d_flow || n_pairs < 1 || n_pairs > h->nb || pitch < w * h->noc)
+    return h ? fail(h, DIS_ERR_INVALID_ARG, "bad argument (1..%d pairs)", h->nb) : DIS_ERR_INVALID_ARG;
+  for (int i = 0; i < n_pairs; ++i)
+    if (!d_a[i] || !d_b[i] || !d_flow[i]) return fail(h, DIS_ERR_INVALID_ARG, "null pointer in pair %d", i);
+  CU(h, cudaSetDevice(h->device));
+  int rc = plan(h, w, h_img);
+  if (rc != DIS_OK) return rc;
+  reset_timings(h);
+  rc = enqueue_run_device_batch(h, n_pairs, d_a, d_b, pitch, reinterpret_cast<float2* const*>(d_flow));
   h->in_flight = rc == DIS_OK;
   return rc;
 }

@@ -12,7 +12,9 @@ namespace {
 // source taps of each pixel come from L1.  Same expressions, in the same order, as a per-pixel evaluation.
 __global__ void __launch_bounds__(256) k_finish(const float2* __restrict__ fl, int wl, int hl, int lv_l,
                                                 int left, int top, int w_org, int h_org,
-                                                const Mailbox* __restrict__ mb) {
+                                                const Mailbox* __restrict__ mb, size_t bstride) {
+  fl = bshift(fl, (size_t)blockIdx.z * bstride);  // blockIdx.z = pair of a batched handle
+  mb = bshift(mb, (size_t)blockIdx.z * bstride);
   float2* __restrict__ out = mb->out;
   const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -69,7 +71,9 @@ __global__ void __launch_bounds__(256) k_finish(const float2* __restrict__ fl, i
 // (horizontal lerp of the pre-scaled samples, then vertical lerp), so the result is bit-identical.  Blocks that
 // touch the border clamps or the crop edge fall back to the per-pixel form.
 __global__ void __launch_bounds__(256) k_finish_x4(const float2* __restrict__ fl, int wl, int hl, int left, int top,
-                                                   int w_org, int h_org, const Mailbox* __restrict__ mb) {
+                                                   int w_org, int h_org, const Mailbox* __restrict__ mb, size_t bstride) {
+  fl = bshift(fl, (size_t)blockIdx.z * bstride);  // blockIdx.z = pair of a batched handle
+  mb = bshift(mb, (size_t)blockIdx.z * bstride);
   float2* __restrict__ out = mb->out;
   const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y * blockDim.y + threadIdx.y;
   const int x0 = bx * 4, y0 = by * 4;
@@ -149,14 +153,14 @@ __global__ void __launch_bounds__(256) k_finish_x4(const float2* __restrict__ fl
 }  // namespace
 
 void launch_finish(const float2* flow_l, int wl, int hl, int lv_l, int left, int top, int w_org, int h_org,
-                   const Mailbox* mb, cudaStream_t st) {
+                   const Mailbox* mb, int nb, size_t bstride, cudaStream_t st) {
   if (lv_l == 2 && (left & 3) == 0 && (top & 3) == 0) {
-    dim3 block(32, 8), grid((w_org + 127) / 128, (h_org + 31) / 32);
-    k_finish_x4<<<grid, block, 0, st>>>(flow_l, wl, hl, left, top, w_org, h_org, mb);
+    dim3 block(32, 8), grid((w_org + 127) / 128, (h_org + 31) / 32, nb);
+    k_finish_x4<<<grid, block, 0, st>>>(flow_l, wl, hl, left, top, w_org, h_org, mb, bstride);
     return;
   }
-  dim3 block(32, 8), grid((w_org + 127) / 128, (h_org + 7) / 8);
-  k_finish<<<grid, block, 0, st>>>(flow_l, wl, hl, lv_l, left, top, w_org, h_org, mb);
+  dim3 block(32, 8), grid((w_org + 127) / 128, (h_org + 7) / 8, nb);
+  k_finish<<<grid, block, 0, st>>>(flow_l, wl, hl, lv_l, left, top, w_org, h_org, mb, bstride);
 }
 
 }  // namespace dis

@@ -58,6 +58,15 @@ struct Win {
 // re-read per iteration instead of being held in registers.
 template <int P, bool L2, int NC>
 __global__ void __launch_bounds__(kPsThreads) k_patch_search(const PatchSearchArgs a) {
+  // batched handles: blockIdx.y = pair, all buffers of that pair sit a.g.bstride bytes further (common.cuh)
+  const size_t boff = (size_t)blockIdx.y * a.g.bstride;
+  const float* __restrict__ pI0 = bshift(a.I0, boff);
+  const float* __restrict__ pI0x = bshift(a.I0x, boff);
+  const float* __restrict__ pI0y = bshift(a.I0y, boff);
+  const float* __restrict__ pI1 = bshift(a.I1, boff);
+  const float2* __restrict__ pcoarse = bshift(a.flow_coarse, boff);
+  float2* __restrict__ ppflow = bshift(a.pflow, boff);
+  float* __restrict__ ppweight = bshift(a.pweight, boff);
   constexpr int N = P * P * NC;
   constexpr int PW = P * NC;            // floats per patch row
   constexpr int NI = N / 8;             // chain length
@@ -105,16 +114,16 @@ __global__ void __launch_bounds__(kPsThreads) k_patch_search(const PatchSearchAr
 #pragma unroll
     for (int i = 0; i < NE; ++i) {
       const size_t o = base + eoff(i);
-      T[i] = __ldg(a.I0 + o);
-      GX[i] = __ldg(a.I0x + o);
-      GY[i] = __ldg(a.I0y + o);
+      T[i] = __ldg(pI0 + o);
+      GX[i] = __ldg(pI0x + o);
+      GY[i] = __ldg(pI0y + o);
     }
   }
   if (a.o.patnorm > 0) {
     float ch = 0.0f, ex = 0.0f;
 #pragma unroll
     for (int i = 0; i < NE; ++i) {
-      const float t = REG ? T[i] : __ldg(a.I0 + base + eoff(i));
+      const float t = REG ? T[i] : __ldg(pI0 + base + eoff(i));
       if (i == 0) ch = t; else if (i < NI) ch = ch + t; else ex = t;
     }
     tmean = octet_reduce<EX>(ch, ex) / (float)N;
@@ -129,8 +138,8 @@ __global__ void __launch_bounds__(kPsThreads) k_patch_search(const PatchSearchAr
     float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, e0 = 0.0f, e1 = 0.0f, e2 = 0.0f;
 #pragma unroll
     for (int i = 0; i < NE; ++i) {
-      const float gx_ = REG ? GX[i] : __ldg(a.I0x + base + eoff(i));
-      const float gy_ = REG ? GY[i] : __ldg(a.I0y + base + eoff(i));
+      const float gx_ = REG ? GX[i] : __ldg(pI0x + base + eoff(i));
+      const float gy_ = REG ? GY[i] : __ldg(pI0y + base + eoff(i));
       if (i == 0) {
         c0 = gx_ * gx_; c1 = gx_ * gy_; c2 = gy_ * gy_;
       } else if (i < NI) {
@@ -162,9 +171,9 @@ __global__ void __launch_bounds__(kPsThreads) k_patch_search(const PatchSearchAr
 
   // ---- InitializeFromCoarserOF (patchgrid.cpp:195-211)
   float pinx = 0.0f, piny = 0.0f;
-  if (a.flow_coarse != nullptr) {
+  if (pcoarse != nullptr) {
     const int x = (int)floorf((float)cx / 2), y = (int)floorf((float)cy / 2);
-    const float2 f = __ldg(a.flow_coarse + (size_t)y * (a.g.w / 2) + x);
+    const float2 f = __ldg(pcoarse + (size_t)y * (a.g.w / 2) + x);
     pinx = f.x * 2;
     piny = f.y * 2;
   }
@@ -199,7 +208,7 @@ __global__ void __launch_bounds__(kPsThreads) k_patch_search(const PatchSearchAr
     float* wrow = win + c * 4;
 #pragma unroll 4
     for (int wy = 0; wy < WIN; ++wy) {
-      const float* src = a.I1 + (size_t)min(max(wy0 + wy, 0), th1) * pitch;
+      const float* src = pI1 + (size_t)min(max(wy0 + wy, 0), th1) * pitch;
 #pragma unroll
       for (int u = 0; u < NCOL; ++u)
         if (c + 8 * u < WIN) wrow[32 * u] = __ldg(src + xs[u]);
@@ -256,7 +265,7 @@ __global__ void __launch_bounds__(kPsThreads) k_patch_search(const PatchSearchAr
       const float* tbase = wb + (trow * WIN + tcol) * 4;
       // NC > 1: taps straight from the padded target image (the position is inside [lb, ub], so the
       // p x p footprint plus its left/upper neighbours lies inside the padding)
-      const float* gb = a.I1 + (size_t)(posy + pad + LB) * pitch + (posx + pad + LB) * NC;
+      const float* gb = pI1 + (size_t)(posy + pad + LB) * pitch + (posx + pad + LB) * NC;
       float ch = 0.0f;
 #pragma unroll
       for (int i = 0; i < NE; ++i) {
@@ -283,7 +292,7 @@ __global__ void __launch_bounds__(kPsThreads) k_patch_search(const PatchSearchAr
 #pragma unroll
       for (int i = 0; i < NE; ++i) {
         float d = R[i] - m;
-        d = d - (REG ? T[i] : __ldg(a.I0 + base + eoff(i)) - tmean);
+        d = d - (REG ? T[i] : __ldg(pI0 + base + eoff(i)) - tmean);
         if (!L2) {
           if (a.o.costfct == 1)
             d = copysignf(sqrtf(fabsf(d)), d);
@@ -292,8 +301,8 @@ __global__ void __launch_bounds__(kPsThreads) k_patch_search(const PatchSearchAr
         }
         const float ad = fabsf(d);
         R[i] = d;  // |d| is taken when the weights are written out
-        const float tx = (REG ? GX[i] : __ldg(a.I0x + base + eoff(i))) * d;
-        const float ty = (REG ? GY[i] : __ldg(a.I0y + base + eoff(i))) * d;
+        const float tx = (REG ? GX[i] : __ldg(pI0x + base + eoff(i))) * d;
+        const float ty = (REG ? GY[i] : __ldg(pI0y + base + eoff(i))) * d;
         if (i == 0) {
           cgx = tx; cgy = ty; cab = ad;
         } else if (i < NI) {
@@ -329,8 +338,8 @@ __global__ void __launch_bounds__(kPsThreads) k_patch_search(const PatchSearchAr
 
   // ---- results: p_iter and the weight patch (read by AggregateFlowDense)
   if (live) {
-    if (c == 0) a.pflow[ip] = make_float2(px, py);
-    float* pw = a.pweight + (size_t)ip * N;
+    if (c == 0) ppflow[ip] = make_float2(px, py);
+    float* pw = ppweight + (size_t)ip * N;
 #pragma unroll
     for (int i = 0; i < NI; ++i) pw[8 * i + c] = oob_start ? 0.0f : fabsf(R[i]);
     if (EX && c < 4) pw[8 * NI + c] = oob_start ? 0.0f : fabsf(R[NE - 1]);
@@ -344,13 +353,13 @@ int launch_p(const PatchSearchArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)(threads / 8) * Win<P>::SIZE * sizeof(float);
   if (a.o.noc == 3) {
     if (a.o.costfct == 0)
-      k_patch_search<P, true, 3><<<blocks, threads, 0, st>>>(a);
+      k_patch_search<P, true, 3><<<dim3(blocks, a.g.nb), threads, 0, st>>>(a);
     else
-      k_patch_search<P, false, 3><<<blocks, threads, 0, st>>>(a);
+      k_patch_search<P, false, 3><<<dim3(blocks, a.g.nb), threads, 0, st>>>(a);
   } else if (a.o.costfct == 0)
-    k_patch_search<P, true, 1><<<blocks, threads, smem, st>>>(a);
+    k_patch_search<P, true, 1><<<dim3(blocks, a.g.nb), threads, smem, st>>>(a);
   else
-    k_patch_search<P, false, 1><<<blocks, threads, smem, st>>>(a);
+    k_patch_search<P, false, 1><<<dim3(blocks, a.g.nb), threads, smem, st>>>(a);
   return 0;
 }
 

@@ -24,6 +24,7 @@ struct SrcU8 {
   int which;
   const uint8_t* p;
   int w_org, h_org, pitch, left, top;
+  __device__ __forceinline__ void shift(size_t off) { mb = bshift(mb, off); }
   __device__ __forceinline__ void resolve() {
     p = which ? mb->b : mb->a;
     pitch = mb->pitch;
@@ -39,6 +40,7 @@ template <int NC>
 struct SrcDown {  // 2x2 mean of the finer level (padded array, pad offset applied)
   const float* p;
   int pitch, pad;
+  __device__ __forceinline__ void shift(size_t off) { p = bshift(p, off); }
   __device__ __forceinline__ void resolve() {}
   __device__ __forceinline__ float at(int x, int y, int ch) const {
     const float* r0 = p + (size_t)(2 * y + pad) * pitch + (2 * x + pad) * NC + ch;
@@ -52,6 +54,7 @@ template <int NC>
 struct SrcPlain {  // unpadded level image (output of k_block_mean)
   const float* p;
   int w;
+  __device__ __forceinline__ void shift(size_t off) { p = bshift(p, off); }
   __device__ __forceinline__ void resolve() {}
   __device__ __forceinline__ float at(int x, int y, int ch) const { return __ldg(p + ((size_t)y * w + x) * NC + ch); }
 };
@@ -62,14 +65,17 @@ struct SrcPlain {  // unpadded level image (output of k_block_mean)
 // to the level-by-level result.  The block is taken from the replicate-padded level-0 image (run_dense.cpp:298-311),
 // i.e. source coordinates are clamped.  Saves writing and re-reading the levels below lv_l that nothing else uses.
 template <int NC>
-__global__ void __launch_bounds__(256) k_block_mean(const Mailbox* __restrict__ mb, int L, int w_org, int h_org,
+__global__ void __launch_bounds__(256) k_block_mean(const Mailbox* __restrict__ mb0, int L, int w_org, int h_org,
                                                     int left, int top, int w, int h, float* __restrict__ out_a,
-                                                    float* __restrict__ out_b) {
+                                                    float* __restrict__ out_b, size_t bstride) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= w || y >= h) return;
-  const uint8_t* __restrict__ src = blockIdx.z ? mb->b : mb->a;
-  float* __restrict__ out = blockIdx.z ? out_b : out_a;
+  const size_t boff = (size_t)(blockIdx.z >> 1) * bstride;  // grid.z = 2 * pair + frame
+  const Mailbox* __restrict__ mb = bshift(mb0, boff);
+  const bool second = blockIdx.z & 1;
+  const uint8_t* __restrict__ src = second ? mb->b : mb->a;
+  float* __restrict__ out = bshift(second ? out_b : out_a, boff);
   const int pitch = mb->pitch, B = 1 << L;
   const int x0 = x * B - left, y0 = y * B - top;
   unsigned acc[NC];
@@ -100,16 +106,18 @@ __global__ void __launch_bounds__(256) k_block_mean(const Mailbox* __restrict__ 
 template <int NC, typename Src>
 __global__ void __launch_bounds__(256) k_pyr_level(Src sa, Src sb, int w, int h, int pad, int pitch,
                                                    int tw, int th, float* Ia, float* Iax, float* Iay,
-                                                   float* Ib, float* Ibx, float* Iby) {
+                                                   float* Ib, float* Ibx, float* Iby, size_t bstride) {
   const int F0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;  // first float column of this thread
   const int Y = blockIdx.y * blockDim.y + threadIdx.y;
   if (F0 >= pitch || Y >= th) return;
-  const bool second = blockIdx.z == 1;
+  const bool second = blockIdx.z & 1;  // grid.z = 2 * pair + frame
+  const size_t boff = (size_t)(blockIdx.z >> 1) * bstride;
   Src s = second ? sb : sa;
+  s.shift(boff);
   s.resolve();
-  float* I = second ? Ib : Ia;
-  float* Gx = second ? Ibx : Iax;
-  float* Gy = second ? Iby : Iay;
+  float* I = bshift(second ? Ib : Ia, boff);
+  float* Gx = bshift(second ? Ibx : Iax, boff);
+  float* Gy = bshift(second ? Iby : Iay, boff);
   const int y = min(max(Y - pad, 0), h - 1);
   const bool yin = (Y >= pad) && (Y < pad + h);
   float vi[4], vx[4], vy[4];
@@ -143,9 +151,9 @@ template <int NC, typename Src>
 void launch(Src sa, Src sb, const LevelGeom& g, float* Ia, float* Iax, float* Iay, float* Ib,
             float* Ibx, float* Iby, cudaStream_t st) {
   dim3 block(64, 4);
-  dim3 grid((g.pitch / 4 + block.x - 1) / block.x, (g.th + block.y - 1) / block.y, 2);
+  dim3 grid((g.pitch / 4 + block.x - 1) / block.x, (g.th + block.y - 1) / block.y, 2 * g.nb);
   k_pyr_level<NC, Src><<<grid, block, 0, st>>>(sa, sb, g.w, g.h, g.pad, g.pitch, g.tw, g.th, Ia, Iax, Iay,
-                                               Ib, Ibx, Iby);
+                                               Ib, Ibx, Iby, g.bstride);
 }
 
 }  // namespace
@@ -159,6 +167,20 @@ __global__ void k_set_mailbox(Mailbox* mb, const uint8_t* a, const uint8_t* b, f
 
 void launch_set_mailbox(Mailbox* mb, const uint8_t* a, const uint8_t* b, float2* out, int pitch, cudaStream_t st) {
   k_set_mailbox<<<1, 1, 0, st>>>(mb, a, b, out, pitch);
+}
+
+__global__ void k_set_mailboxes(Mailbox* mb0, size_t bstride, int nb, const MailboxBatch m, int pitch) {
+  const int b = threadIdx.x;
+  if (b >= nb) return;
+  Mailbox* mb = bshift(mb0, (size_t)b * bstride);
+  mb->a = m.a[b];
+  mb->b = m.b[b];
+  mb->out = m.out[b];
+  mb->pitch = pitch;
+}
+
+void launch_set_mailboxes(Mailbox* mb0, size_t bstride, int nb, const MailboxBatch& m, int pitch, cudaStream_t st) {
+  k_set_mailboxes<<<1, kMaxBatch, 0, st>>>(mb0, bstride, nb, m, pitch);
 }
 
 void launch_level0(const Mailbox* mb, int w_org, int h_org, int left, int top, const LevelGeom& g, float* Ia,
@@ -177,13 +199,13 @@ void launch_level0(const Mailbox* mb, int w_org, int h_org, int left, int top, c
 void launch_first_level(const Mailbox* mb, int L, int w_org, int h_org, int left, int top, const LevelGeom& g,
                         float* bm_a, float* bm_b, float* Ia, float* Iax, float* Iay, float* Ib, float* Ibx, float* Iby,
                         cudaStream_t st) {
-  dim3 block(32, 8), grid((g.w + 31) / 32, (g.h + 7) / 8, 2);
+  dim3 block(32, 8), grid((g.w + 31) / 32, (g.h + 7) / 8, 2 * g.nb);
   if (g.noc == 3) {
-    k_block_mean<3><<<grid, block, 0, st>>>(mb, L, w_org, h_org, left, top, g.w, g.h, bm_a, bm_b);
+    k_block_mean<3><<<grid, block, 0, st>>>(mb, L, w_org, h_org, left, top, g.w, g.h, bm_a, bm_b, g.bstride);
     SrcPlain<3> sa{bm_a, g.w}, sb{bm_b, g.w};
     launch<3>(sa, sb, g, Ia, Iax, Iay, Ib, Ibx, Iby, st);
   } else {
-    k_block_mean<1><<<grid, block, 0, st>>>(mb, L, w_org, h_org, left, top, g.w, g.h, bm_a, bm_b);
+    k_block_mean<1><<<grid, block, 0, st>>>(mb, L, w_org, h_org, left, top, g.w, g.h, bm_a, bm_b, g.bstride);
     SrcPlain<1> sa{bm_a, g.w}, sb{bm_b, g.w};
     launch<1>(sa, sb, g, Ia, Iax, Iay, Ib, Ibx, Iby, st);
   }

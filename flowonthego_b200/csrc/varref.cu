@@ -50,10 +50,15 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v,
 __global__ void __launch_bounds__(256) k_warp(int w, int h, int pad, int pitch, int noc, const float* __restrict__ I0,
                                               const float* __restrict__ I1, const float2* __restrict__ flow,
                                               float* __restrict__ avg, float* __restrict__ Iz,
-                                              float* __restrict__ mask) {
+                                              float* __restrict__ mask, size_t bstride) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   if (i >= w || j >= h) return;
+  {  // blockIdx.z = pair of a batched handle (common.cuh)
+    const size_t boff = (size_t)blockIdx.z * bstride;
+    I0 = bshift(I0, boff); I1 = bshift(I1, boff); flow = bshift(flow, boff);
+    avg = bshift(avg, boff); Iz = bshift(Iz, boff); mask = bshift(mask, boff);
+  }
   const int o = j * w + i, n = w * h;
   const float2 f = flow[o];
   const float xx = (float)i + f.x, yy = (float)j + f.y;
@@ -112,12 +117,17 @@ __device__ __forceinline__ float conv_v5(const float* __restrict__ s, int w, int
 __global__ void __launch_bounds__(256) k_deriv1(int w, int h, const float* __restrict__ avg,
                                                 const float* __restrict__ Iz, float* __restrict__ Ix,
                                                 float* __restrict__ Iy, float* __restrict__ Ixz,
-                                                float* __restrict__ Iyz) {
+                                                float* __restrict__ Iyz, int noc, size_t bstride) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   if (i >= w || j >= h) return;
   const int o = j * w + i;
-  const size_t pl = (size_t)blockIdx.z * w * h;  // colour plane
+  {  // blockIdx.z = pair * noc + colour plane
+    const size_t boff = (size_t)(blockIdx.z / noc) * bstride;
+    avg = bshift(avg, boff); Iz = bshift(Iz, boff); Ix = bshift(Ix, boff); Iy = bshift(Iy, boff);
+    Ixz = bshift(Ixz, boff); Iyz = bshift(Iyz, boff);
+  }
+  const size_t pl = (size_t)(blockIdx.z % noc) * w * h;  // colour plane
   avg += pl; Iz += pl; Ix += pl; Iy += pl; Ixz += pl; Iyz += pl;
   Ix[o] = conv_h5(avg, w, i, j * w);
   Iy[o] = conv_v5(avg, w, h, i, j);
@@ -127,12 +137,16 @@ __global__ void __launch_bounds__(256) k_deriv1(int w, int h, const float* __res
 
 __global__ void __launch_bounds__(256) k_deriv2(int w, int h, const float* __restrict__ Ix,
                                                 const float* __restrict__ Iy, float* __restrict__ Ixx,
-                                                float* __restrict__ Ixy, float* __restrict__ Iyy) {
+                                                float* __restrict__ Ixy, float* __restrict__ Iyy, int noc, size_t bstride) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   if (i >= w || j >= h) return;
   const int o = j * w + i;
-  const size_t pl = (size_t)blockIdx.z * w * h;  // colour plane
+  {  // blockIdx.z = pair * noc + colour plane
+    const size_t boff = (size_t)(blockIdx.z / noc) * bstride;
+    Ix = bshift(Ix, boff); Iy = bshift(Iy, boff); Ixx = bshift(Ixx, boff); Ixy = bshift(Ixy, boff); Iyy = bshift(Iyy, boff);
+  }
+  const size_t pl = (size_t)(blockIdx.z % noc) * w * h;  // colour plane
   Ix += pl; Iy += pl; Ixx += pl; Ixy += pl; Iyy += pl;
   Ixx[o] = conv_h5(Ix, w, i, j * w);
   Ixy[o] = conv_v5(Ix, w, h, i, j);
@@ -164,6 +178,7 @@ struct AssembleArgs {
   float4 *coefA, *coefB;  // {a11,a12,a22,horiz}, {b1,b2,vert,0}, wavefront-major
   int* prog;              // SOR flags: [0] epoch, [1] ticket, [2..2+n_prog) per-item progress counters
   int n_prog;
+  size_t bstride;         // batched handles: blockIdx.z = pair
 };
 
 __device__ __forceinline__ float2 uu_at(const AssembleArgs& a, int i, int j, float2* d_out) {
@@ -184,7 +199,16 @@ __device__ __forceinline__ float2 uu_at(const AssembleArgs& a, int i, int j, flo
 // step that live in this tile are written as one contiguous 128-byte run.
 constexpr int ATX = 32, ATY = 8;
 
-__global__ void __launch_bounds__(ATX* ATY) k_assemble(const AssembleArgs a) {
+__global__ void __launch_bounds__(ATX* ATY) k_assemble(const AssembleArgs a_in) {
+  AssembleArgs a = a_in;
+  {
+    const size_t boff = (size_t)blockIdx.z * a.bstride;
+    a.flow = bshift(a.flow, boff); a.du4 = bshift(a.du4, boff); a.mask = bshift(a.mask, boff);
+    a.Ix = bshift(a.Ix, boff); a.Iy = bshift(a.Iy, boff); a.Iz = bshift(a.Iz, boff);
+    a.Ixx = bshift(a.Ixx, boff); a.Ixy = bshift(a.Ixy, boff); a.Iyy = bshift(a.Iyy, boff);
+    a.Ixz = bshift(a.Ixz, boff); a.Iyz = bshift(a.Iyz, boff);
+    a.coefA = bshift(a.coefA, boff); a.coefB = bshift(a.coefB, boff); a.prog = bshift(a.prog, boff);
+  }
   __shared__ float2 uu_s[ATY + 4][ATX + 4];
   __shared__ float2 du_s[ATY][ATX];
   __shared__ float s_s[ATY + 2][ATX + 2];
@@ -379,6 +403,7 @@ struct SorArgs {
   const float4 *coefA, *coefB;  // wavefront-major [K][nsp][32]
   float4* du4;                  // wavefront-major records {du, dv, tag, -}: [K+1][nsp][32]
   int* prog;                    // [0] epoch, [1] ticket, [2 + t*K + k] pacing hint: completed steps of item (t,k)
+  size_t bstride;               // batched handles: blockIdx.y = pair
 };
 
 // kG = steps per group: prefetch / validation / pacing-hint granularity, = steps per TMA chunk of the coefficient
@@ -431,8 +456,14 @@ __device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
 }
 
 template <int kG>
-__global__ void __launch_bounds__(32) k_sor_wavefront(const SorArgs a) {
+__global__ void __launch_bounds__(32) k_sor_wavefront(const SorArgs a_in) {
   constexpr int kCH = kG, kRD = 2 * kG;
+  SorArgs a = a_in;
+  {
+    const size_t boff = (size_t)blockIdx.y * a.bstride;
+    a.coefA = bshift(a.coefA, boff); a.coefB = bshift(a.coefB, boff); a.du4 = bshift(a.du4, boff);
+    a.prog = bshift(a.prog, boff);
+  }
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* const sA = smem_raw;                                          // [kNS*kCH][32] float4
   unsigned char* const sB = smem_raw + (size_t)kNS * kCH * 512;                // [kNS*kCH][32] float4
@@ -699,10 +730,13 @@ __global__ void __launch_bounds__(32) k_sor_wavefront(const SorArgs a) {
 }
 
 // final flow = wx + du (refine_variational.cpp:212-221)
-__global__ void __launch_bounds__(256) k_update(int w, int h, float2* __restrict__ flow, const float4* __restrict__ du4) {
+__global__ void __launch_bounds__(256) k_update(int w, int h, float2* __restrict__ flow, const float4* __restrict__ du4,
+                                                size_t bstride) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   if (i >= w || j >= h) return;
+  flow = bshift(flow, (size_t)blockIdx.z * bstride);
+  du4 = bshift(du4, (size_t)blockIdx.z * bstride);
   const int o = j * w + i;
   const float2 f = flow[o];
   const float4 d = du4[Skew(w, h).at(i, j)];
@@ -730,19 +764,21 @@ int launch_varref(const LevelGeom& g, const VarParams& v, const float* I0, const
   const int w = g.w, h = g.h, n = w * h;
   if (w < 2 || h < 4 || v.n_solver < 1 || v.n_solver > 256) return -1;  // reference would take its slow path / read out of range
   int launches = 0;
-  dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
+  const int nb = g.nb;  // pairs per launch (batched handles): rides on grid.z (grid.y for the SOR)
+  const size_t bs = g.bstride;
+  dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8, nb);
   // algorithmic bytes per SURVEY.md section 8(d): warp+mask 28 B/px, derivative stack 40 B/px
   {
     ProfScope ps(prof, "k_warp", g.lv, 28.0 * n);
-    k_warp<<<grid, block, 0, st>>>(w, h, g.pad, g.pitch, g.noc, I0, I1, flow, b.avg, b.Iz, b.mask);
+    k_warp<<<grid, block, 0, st>>>(w, h, g.pad, g.pitch, g.noc, I0, I1, flow, b.avg, b.Iz, b.mask, bs);
   }
   {
     ProfScope ps(prof, "k_deriv1", g.lv, 24.0 * n);
-    k_deriv1<<<dim3(grid.x, grid.y, g.noc), block, 0, st>>>(w, h, b.avg, b.Iz, b.Ix, b.Iy, b.Ixz, b.Iyz);
+    k_deriv1<<<dim3(grid.x, grid.y, g.noc * nb), block, 0, st>>>(w, h, b.avg, b.Iz, b.Ix, b.Iy, b.Ixz, b.Iyz, g.noc, bs);
   }
   {
     ProfScope ps(prof, "k_deriv2", g.lv, 16.0 * n);
-    k_deriv2<<<dim3(grid.x, grid.y, g.noc), block, 0, st>>>(w, h, b.Ix, b.Iy, b.Ixx, b.Ixy, b.Iyy);
+    k_deriv2<<<dim3(grid.x, grid.y, g.noc * nb), block, 0, st>>>(w, h, b.Ix, b.Iy, b.Ixx, b.Ixy, b.Iyy, g.noc, bs);
   }
   launches += 3;
   if (v.n_inner <= 0) return launches;
@@ -750,30 +786,31 @@ int launch_varref(const LevelGeom& g, const VarParams& v, const float* I0, const
   const int K = sk.K, T = v.n_solver;
   size_t n_coef4, n_du4, n_prog;
   varref_sizes(w, h, T, &n_coef4, &n_du4, &n_prog);
-  cudaMemsetAsync(b.du4, 0, sizeof(float4) * n_du4, st);  // du = dv = 0 (image_erase, refine_variational.cpp:184-185)
+  // du = dv = 0 (image_erase, refine_variational.cpp:184-185), for every pair of the batch
+  cudaMemset2DAsync(b.du4, nb > 1 ? bs : sizeof(float4) * n_du4, 0, sizeof(float4) * n_du4, nb, st);
   for (int it = 0; it < v.n_inner; ++it) {
     AssembleArgs aa{w, h, v.qa, v.hg, v.hd, it == 0 ? 1 : 0, g.noc, flow, b.du4,
                     b.mask, b.Ix, b.Iy, b.Iz, b.Ixx, b.Ixy, b.Iyy, b.Ixz, b.Iyz, b.coefA, b.coefB, b.progress,
-                    T * K};
+                    T * K, bs};
     {
       // smoothness 16 + data term 64 + sub_laplacian 32 + flow update 24 B/px
       ProfScope ps(prof, "k_assemble", g.lv, 136.0 * n);
       k_assemble<<<grid, block, 0, st>>>(aa);
     }
-    SorArgs sa{w, h, T, K, v.omega, b.coefA, b.coefB, b.du4, b.progress};
+    SorArgs sa{w, h, T, K, v.omega, b.coefA, b.coefB, b.du4, b.progress, bs};
     {
       // each sweep reads 9 arrays and writes 2: 44 B/px
       ProfScope ps(prof, "k_sor_wavefront", g.lv, 44.0 * T * n);
       if (v.sor_group == 16)
-        k_sor_wavefront<16><<<T * K, 32, sor_smem<16>(), st>>>(sa);
+        k_sor_wavefront<16><<<dim3(T * K, nb), 32, sor_smem<16>(), st>>>(sa);
       else
-        k_sor_wavefront<8><<<T * K, 32, sor_smem<8>(), st>>>(sa);
+        k_sor_wavefront<8><<<dim3(T * K, nb), 32, sor_smem<8>(), st>>>(sa);
     }
     launches += 2;
   }
   {
     ProfScope ps(prof, "k_update", g.lv, 8.0 * n);
-    k_update<<<grid, block, 0, st>>>(w, h, flow, b.du4);
+    k_update<<<grid, block, 0, st>>>(w, h, flow, b.du4, bs);
   }
   return launches + 1;
 }

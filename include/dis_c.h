@@ -178,6 +178,18 @@ int dis_read_image_gray(const char* path, uint8_t* out, size_t cap, int* w, int*
 /* Colour build (kroeger/run_dense.cpp:203-206 cv::imread(.., COLOR)): interleaved BGR, 3*w*h bytes. */
 int dis_read_image_bgr(const char* path, uint8_t* out, size_t cap, int* w, int* h);
 
+/* ---- batched handles: several pairs per kernel launch ----------------------------------------------------- */
+/* dis_create_batch makes a handle whose every kernel launch serves `batch` (1..8) pairs at once: the workspace is
+ * replicated `batch` times and the pair index rides on a grid dimension, so a pair costs 1/batch of the launches
+ * (88 at 1080p) and the latency-bound coarse levels get `batch` times the parallelism.  Results per pair are
+ * bit-identical to dis_run_u8.  dis_submit_u8_device_batch takes arrays of n_pairs <= batch device pointers (same
+ * w, h, pitch for all); asynchronous on the handle's stream, dis_wait() waits for all pairs.  The single-pair
+ * entry points also work on such a handle (they use slot 0; the other slots idle along). */
+int dis_create_batch(const dis_params* params, int channels, int max_w, int max_h, int device, int batch, dis_handle** out);
+int dis_batch_size(const dis_handle* h);
+int dis_submit_u8_device_batch(dis_handle* h, int n_pairs, const uint8_t* const* d_a, const uint8_t* const* d_b, int w,
+                               int h_img, int pitch, float* const* d_flow);
+
 /* ---- groups: several pairs per launch ----------------------------------------------------------------- */
 /* A group owns n engine handles and records their runs as n parallel branches of one CUDA graph, launched on one
  * stream: the device runs n times as many dependent kernel chains per hardware work queue.  Each

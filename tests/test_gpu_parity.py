@@ -296,6 +296,37 @@ def test_group_of_pairs_per_launch():
             g.submit_u8_device([0], [0], w, h, w, [0])
 
 
+@pytest.mark.parametrize("channels,usefbcon,batch", [(1, 0, 4), (1, 1, 3), (3, 0, 2)])
+def test_batched_handle(channels, usefbcon, batch):
+    """dis_create_batch: every launch serves `batch` pairs; each pair equals a separate run, also with fewer pairs
+    than slots and through the single-pair entry points."""
+    import torch
+    w, h = 322, 198
+    p = params(2, 1024, lv_f=3, lv_l=1, usefbcon=usefbcon)
+    mk = synth_pair if channels == 1 else synth_pair_bgr
+    pairs = [mk(w, h, seed=40 + k)[:2] for k in range(batch)]
+    refs = [port.run_u8(x[0], x[1], p.to_dict()) for x in pairs]
+    da = [torch.from_numpy(x[0]).cuda() for x in pairs]
+    db = [torch.from_numpy(x[1]).cuda() for x in pairs]
+    out = torch.zeros((batch, h, w, 2), dtype=torch.float32, device="cuda")
+    with F.Engine(p, w, h, channels=channels, batch=batch) as e:
+        for rep in range(2):  # capture, then replay
+            out.zero_()
+            e.submit_u8_device_batch([x.data_ptr() for x in da], [x.data_ptr() for x in db], w, h, w * channels,
+                                     [out[k].data_ptr() for k in range(batch)])
+            e.wait()
+            for k in range(batch):
+                assert bits_differ(out[k].cpu().numpy(), refs[k]) == 0, (rep, k)
+        out.zero_()
+        e.submit_u8_device_batch([da[-1].data_ptr()], [db[-1].data_ptr()], w, h, w * channels, [out[0].data_ptr()])
+        e.wait()
+        assert bits_differ(out[0].cpu().numpy(), refs[-1]) == 0
+        assert float(out[1:].abs().sum()) == 0.0  # idle slots write to their own scratch
+        assert bits_differ(e.run_u8(pairs[0][0], pairs[0][1]), refs[0]) == 0  # host-buffer entry point, slot 0
+    with pytest.raises(F.DisError):
+        F.Engine(p, w, h, batch=9)
+
+
 def test_async_and_device_entry_points():
     import torch
     a, b, _ = synth_pair(320, 240, seed=4)
