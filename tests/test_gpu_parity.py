@@ -456,3 +456,41 @@ def test_rgb_full_size_1080p():
     assert_flow_parity(flow, port.run_u8(a, b, p.to_dict()), 12, 2)
     epe = np.sqrt(((flow - gt) ** 2).sum(-1))[48:-48, 48:-48]
     assert epe.mean() < 0.5, epe.mean()
+
+
+def test_randomized_configurations():
+    """Seeded sweep over sizes (incl. non-multiples of 2^lv_f), patch sizes, overlaps, iteration settings, cost
+    functions, forward-backward merging, refinement settings and channel counts: every result bit-identical."""
+    rng = np.random.default_rng(20261017)
+    ran = 0
+    for case in range(28):
+        ch = 3 if case % 4 == 3 else 1
+        w, h = int(rng.integers(70, 420)), int(rng.integers(60, 300))
+        patchsz = int(rng.choice([4, 6, 8, 10, 12, 14, 16]))
+        lv_f = int(rng.integers(0, 4))
+        while lv_f > 0 and (min(w, h) >> lv_f) < max(8, patchsz // 2 + 2):  # keep the coarsest level meaningful
+            lv_f -= 1
+        lv_l = int(rng.integers(0, lv_f + 1))
+        maxit = int(rng.integers(1, 20))
+        kw = dict(lv_f=lv_f, lv_l=lv_l, patchsz=patchsz, poverl=float(rng.choice([0.0, 0.3, 0.5, 0.75, 0.9])),
+                  maxiter=maxit, miniter=int(rng.integers(0, maxit + 1)), mindprate=float(rng.choice([0.05, 0.2, 0.5])),
+                  mindrrate=float(rng.choice([0.95, 0.8])), minimgerr=float(rng.choice([0.0, 0.5, 2.0])),
+                  usefbcon=int(rng.integers(0, 2)), patnorm=int(rng.integers(0, 2)), costfct=int(rng.integers(0, 3)),
+                  usetvref=int(rng.integers(0, 4) > 0), tv_alpha=float(rng.choice([10.0, 3.0, 30.0])),
+                  tv_gamma=float(rng.choice([10.0, 0.0, 5.0])), tv_delta=float(rng.choice([5.0, 0.0, 1.0])),
+                  tv_innerit=int(rng.integers(0, 3)), tv_solverit=int(rng.integers(1, 6)),
+                  tv_sor=float(rng.choice([1.6, 1.0, 1.9])))
+        p = params(2, 1024, **kw)
+        a, b, _ = (synth_pair if ch == 1 else synth_pair_bgr)(w, h, seed=100 + case, shift=(float(rng.uniform(-6, 6)),
+                                                                                              float(rng.uniform(-4, 4))))
+        try:
+            eng = F.Engine(p, w, h, channels=ch)
+        except F.DisError as ex:  # e.g. coarsest level too small for this patch size: the engine says so
+            assert "too small" in str(ex), (case, kw, str(ex))
+            continue
+        with eng as e:
+            got = e.run_u8(a, b)
+        ref = port.run_u8(a, b, p.to_dict())
+        assert bits_differ(got, ref) == 0, (case, ch, w, h, kw)
+        ran += 1
+    assert ran >= 20
