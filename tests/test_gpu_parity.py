@@ -181,6 +181,23 @@ def test_ragged_and_small_inputs():
         assert bits_differ(flow, port.run_u8(a, b, p.to_dict())) == 0, (w, h)
 
 
+def test_finish_block_kernel_edges():
+    """lv_l = 2 with padding offsets that are multiples of 4 takes the 4x4-block upsampling kernel: sizes whose last
+    block column / row is partial, and sizes small enough that every block touches a border clamp."""
+    for (w, h, lv_f) in ((323, 203, 2), (327, 207, 3), (320, 200, 2), (19, 15, 2), (324, 8, 2)):
+        wp, hp, left, top = F.padded_size(w, h, lv_f)
+        assert left % 4 == 0 and top % 4 == 0
+        a, b, _ = synth_pair(w, h, seed=w + h)
+        p = params(2, 1024, lv_f=lv_f, lv_l=2, patchsz=4 if min(w, h) < 32 else 8)
+        try:
+            eng = F.Engine(p, w, h)
+        except F.DisError as ex:
+            assert "too small" in str(ex)
+            continue
+        with eng as e:
+            assert bits_differ(e.run_u8(a, b), port.run_u8(a, b, p.to_dict())) == 0, (w, h, lv_f)
+
+
 def test_c3_full_size_1080p():
     """C3: 1920x1080 synthetic affine pair, preset 3 + variational; oracle comparison and EPE vs ground truth."""
     a, b, gt = synth_pair(1920, 1080, seed=1)
