@@ -456,7 +456,7 @@ __device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
 }
 
 template <int kG>
-__global__ void __launch_bounds__(32) k_sor_wavefront(const SorArgs a_in) {
+__global__ void __launch_bounds__(32, kG == 8 ? 16 : 8) k_sor_wavefront(const SorArgs a_in) {
   constexpr int kCH = kG, kRD = 2 * kG;
   SorArgs a = a_in;
   {
