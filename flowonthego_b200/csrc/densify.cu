@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) k_bw_anchors(const LevelGeom g, const Opt
 }
 
 template <bool FB>
-__global__ void __launch_bounds__(256) k_densify(const DensifyArgs a) {
+__global__ void __launch_bounds__(256, 2) k_densify(const DensifyArgs a) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= a.g.w || y >= a.g.h) return;

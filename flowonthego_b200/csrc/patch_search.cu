@@ -57,7 +57,7 @@ struct Win {
 // from global memory (L1/L2) instead of a staged window, and for p > 8 the template and gradients are
 // re-read per iteration instead of being held in registers.
 template <int P, bool L2, int NC>
-__global__ void __launch_bounds__(kPsThreads) k_patch_search(const PatchSearchArgs a) {
+__global__ void __launch_bounds__(kPsThreads, (P == 12 && NC == 1) ? 512 / kPsThreads : 1) k_patch_search(const PatchSearchArgs a) {
   // batched handles: blockIdx.y = pair, all buffers of that pair sit a.g.bstride bytes further (common.cuh)
   const size_t boff = (size_t)blockIdx.y * a.g.bstride;
   const float* __restrict__ pI0 = bshift(a.I0, boff);
