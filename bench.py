@@ -12,9 +12,12 @@ frame pairs per GPU.  Independent pairs shard across ranks with no data-path col
 scaling: the per-GPU batch is fixed); torch.distributed (NCCL) is used only for the barrier and the
 max-over-ranks of the device time.
 
-  value : pairs/s with the frames already resident in HBM, results left in HBM
+  value : pairs/s with the frames already resident in HBM, results left in HBM; batched handles
+          (dis_submit_u8_device_batch, --pairs-per-launch pairs per kernel launch, --batch-handles in flight)
   e2e   : pairs/s through the reference-facing C-ABI call dis_submit_u8/dis_wait with pinned HOST
-          buffers (H2D of both frames and D2H of the full-resolution flow inside the timed region)
+          buffers (H2D of both frames and D2H of the full-resolution flow inside the timed region),
+          one pair per call on --streams single-pair handles
+  extras (N=1 unless noted): 4K pair (C4a), the video front end, engine-level output (all N)
   roofline / cpu_baseline : see DESIGN.md; the CPU leg is the reference's own engine (oracle/_ref,
           compiled verbatim) or, if that was not built, the C restatement (oracle/).
 
