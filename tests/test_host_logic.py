@@ -112,3 +112,23 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert "oracle" not in src.replace("# oracle-free", ""), os.path.join(dp, f)
+
+
+def test_cli_binaries_usage_and_loud_failure(tmp_path, golden_dir):
+    """The compiled CLIs exist next to the library, print their usage on bad arguments and -- without a GPU --
+    fail with an error instead of computing anything on the CPU."""
+    import subprocess
+    bindir = os.path.dirname(F.api.__file__)
+    for exe in ("run_dense", "run_dense_rgb", "run_dense_stream", "color_flow", "flow_epe"):
+        r = subprocess.run([os.path.join(bindir, exe)], capture_output=True, text=True)
+        assert r.returncode != 0 and "usage" in (r.stderr + r.stdout).lower(), exe
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return
+    except ImportError:
+        pass
+    a = os.path.join(golden_dir, "alley_0001_gray.png")
+    b = os.path.join(golden_dir, "alley_0002_gray.png")
+    r = subprocess.run([os.path.join(bindir, "run_dense"), a, b, str(tmp_path / "o.flo")], capture_output=True, text=True)
+    assert r.returncode == 1 and "run_dense:" in r.stderr and not (tmp_path / "o.flo").exists()
