@@ -6,8 +6,8 @@ import os as _os
 # context (e.g. before torch touches the GPU), hence at import time as well as at library load
 _os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
-from .api import (DisError, Engine, EngineGroup, FlowStream, flow_epe, flow_to_color, write_png_bgr, OFClass, Params, PARAM_NAMES, lib, padded_size, pinned_empty, read_flo, read_image_bgr, read_image_gray,
+from .api import (DisError, Engine, FlowStream, flow_epe, flow_to_color, write_png_bgr, OFClass, Params, PARAM_NAMES, lib, padded_size, pinned_empty, read_flo, read_image_bgr, read_image_gray,
                   run_dense, write_flo)
 
 __all__ = ["DisError", "Engine", "OFClass", "Params", "PARAM_NAMES", "lib", "padded_size", "pinned_empty",
-           "read_flo", "read_image_bgr", "read_image_gray", "run_dense", "write_flo", "flow_epe", "flow_to_color", "write_png_bgr", "FlowStream", "EngineGroup"]
+           "read_flo", "read_image_bgr", "read_image_gray", "run_dense", "write_flo", "flow_epe", "flow_to_color", "write_png_bgr", "FlowStream"]

@@ -125,21 +125,22 @@ def lib():
         L.dis_host_free.argtypes = [vp]
         L.dis_read_image_gray.argtypes = [ctypes.c_char_p, vp, ctypes.c_size_t, ctypes.POINTER(ip), ctypes.POINTER(ip)]
         L.dis_read_image_bgr.argtypes = L.dis_read_image_gray.argtypes
-        L.dis_group_create.argtypes = [pp, ip, ip, ip, ip, ip, ctypes.POINTER(vp)]
-        L.dis_group_destroy.argtypes = [vp]
-        L.dis_group_destroy.restype = None
-        L.dis_group_submit_u8_device.argtypes = [vp, ip, ctypes.POINTER(vp), ctypes.POINTER(vp), ip, ip, ip, ctypes.POINTER(vp)]
-        L.dis_group_wait.argtypes = [vp]
-        L.dis_group_stream.argtypes = [vp]
-        L.dis_group_stream.restype = vp
-        L.dis_group_last_error.argtypes = [vp]
-        L.dis_group_last_error.restype = ctypes.c_char_p
         L.dis_video_create.argtypes = [pp, ip, ip, ip, ip, ip, ctypes.POINTER(vp)]
         L.dis_video_destroy.argtypes = [vp]
         L.dis_video_destroy.restype = None
         L.dis_video_push.argtypes = [vp, vp, ip, fp]
         L.dis_video_pop.argtypes = [vp, ctypes.POINTER(fp)]
         L.dis_video_pending.argtypes = [vp]
+        L.dis_video_set_output.argtypes = [vp, ip]
+        L.dis_video_flow_size.argtypes = [vp, ctypes.POINTER(ip), ctypes.POINTER(ip)]
+        L.dis_video_flow_size.restype = ctypes.c_size_t
+        L.dis_video_handle.argtypes = [vp, ip]
+        L.dis_video_handle.restype = vp
+        L.dis_level_flow_size.argtypes = [vp, ctypes.POINTER(ip), ctypes.POINTER(ip)]
+        L.dis_copy_level_flow_device.argtypes = [vp, ip, vp]
+        L.dis_copy_level_flows_device.argtypes = [vp, ip, vp]
+        L.dis_level_flow_ptr.argtypes = [vp, ip]
+        L.dis_level_flow_ptr.restype = vp
         L.dis_flow_to_color.argtypes = [fp, ip, ip, ctypes.c_float, ip, vp, fp]
         L.dis_flow_epe.argtypes = [fp, fp, ip, ip, ip, ip, ctypes.POINTER(ctypes.c_double),
                                    ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]
@@ -278,6 +279,23 @@ class Engine:
         keep, self._keep = self._keep, None
         return keep[2] if keep else None
 
+    def level_flow_ptr(self, pair=0):
+        """Device address of the level-lv_l flow of `pair` inside the workspace (dis_level_flow_ptr)."""
+        return lib().dis_level_flow_ptr(self._h, int(pair))
+
+    def level_flow_shape(self):
+        w, h = ctypes.c_int(), ctypes.c_int()
+        _check(lib().dis_level_flow_size(self._h, ctypes.byref(w), ctypes.byref(h)), self._h)
+        return (h.value, w.value, 2)
+
+    def copy_level_flow_device(self, pair, d_dst):
+        """Enqueue a device-to-device copy of the level flow of `pair` to device pointer d_dst on the engine's stream."""
+        _check(lib().dis_copy_level_flow_device(self._h, int(pair), d_dst), self._h)
+
+    def copy_level_flows_device(self, n_pairs, d_dst):
+        """Batched handle: level flows of pairs 0..n_pairs-1 -> contiguous [n_pairs][h_l][w_l][2] at d_dst."""
+        _check(lib().dis_copy_level_flows_device(self._h, int(n_pairs), d_dst), self._h)
+
     def level_flow(self, w, h):
         """Raw engine output (level lv_l, padded size) of the last run_u8."""
         wp, hp, _, _ = padded_size(w, h, self.params.lv_f)
@@ -347,57 +365,14 @@ class Engine:
         return lib().dis_stream(self._h)
 
 
-class EngineGroup:
-    """n pairs per graph launch (dis_group_*): device-resident frames in, device-resident flows out."""
-
-    def __init__(self, params, max_w, max_h, n, device=0, channels=1):
-        self._g = ctypes.c_void_p()
-        self.params = params if isinstance(params, Params) else Params.from_dict(params)
-        self.n = int(n)
-        _check(lib().dis_group_create(ctypes.byref(self.params), int(channels), int(max_w), int(max_h), int(device),
-                                      self.n, ctypes.byref(self._g)), None)
-
-    def close(self):
-        if self._g:
-            lib().dis_group_destroy(self._g)
-            self._g = ctypes.c_void_p()
-
-    def __enter__(self):
-        return self
-
-    def __exit__(self, *a):
-        self.close()
-
-    def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass
-
-    def _err(self, rc):
-        if rc != 0:
-            raise DisError(rc, (lib().dis_group_last_error(self._g) or b"").decode())
-
-    def submit_u8_device(self, d_a, d_b, w, h, pitch, d_flow):
-        """d_a, d_b, d_flow: sequences of device pointers (ints), one per pair (at most n)."""
-        k = len(d_a)
-        arr = ctypes.c_void_p * k
-        self._err(lib().dis_group_submit_u8_device(self._g, k, arr(*d_a), arr(*d_b), w, h, pitch, arr(*d_flow)))
-
-    def wait(self):
-        self._err(lib().dis_group_wait(self._g))
-
-    @property
-    def stream(self):
-        return lib().dis_group_stream(self._g)
-
-
 class FlowStream:
     """Video-stream front end (dis_video_*): push consecutive frames, get one flow per consecutive pair,
-    `depth` pairs in flight on the GPU, every frame uploaded once.  Each flow equals Engine.run_u8 on that
-    pair bit for bit."""
+    `depth` pairs in flight on the GPU, every frame uploaded once.  output="level" (the default for streams):
+    the engine's own output as OFC::OFClass delivers it, (h_pad/2^lv_l, w_pad/2^lv_l, 2) -- equal to
+    Engine.level_flow() of that pair bit for bit; output="full": the full-resolution (h, w, 2) field, equal to
+    Engine.run_u8 on that pair bit for bit."""
 
-    def __init__(self, params, w, h, depth=8, device=0, channels=1):
+    def __init__(self, params, w, h, depth=8, device=0, channels=1, output="level"):
         self._v = ctypes.c_void_p()
         self.params = params if isinstance(params, Params) else Params.from_dict(params)
         self.w, self.h, self.depth, self.channels = int(w), int(h), int(depth), int(channels)
@@ -405,8 +380,18 @@ class FlowStream:
                                       self.depth, ctypes.byref(self._v)), None)
         shape = (self.h, self.w) if self.channels == 1 else (self.h, self.w, self.channels)
         self._frames = [pinned_empty(shape, np.uint8) for _ in range(self.depth + 1)]
-        self._flows = [pinned_empty((self.h, self.w, 2), np.float32) for _ in range(self.depth)]
+        if output not in ("level", "full"):
+            raise ValueError("output must be 'level' or 'full'")
+        _check(lib().dis_video_set_output(self._v, 0 if output == "level" else 1), None)
+        fw, fh = ctypes.c_int(), ctypes.c_int()
+        lib().dis_video_flow_size(self._v, ctypes.byref(fw), ctypes.byref(fh))
+        self.flow_shape = (fh.value, fw.value, 2)
+        self._flows = [pinned_empty(self.flow_shape, np.float32) for _ in range(self.depth)]
         self._n = 0
+
+    def handle(self, k):
+        """k-th engine handle (a dis_handle*, e.g. for lib().dis_stream)."""
+        return lib().dis_video_handle(self._v, int(k))
 
     def close(self):
         if self._v:

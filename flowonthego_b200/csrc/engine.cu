@@ -128,7 +128,8 @@ struct dis_handle {
   KernelProf kprof;
   std::vector<std::vector<Tap>> tapdata;  // [tap][level]
   dis_timings tm{};
-  cudaEvent_t ev[10] = {};
+  cudaEvent_t ev[4] = {};  // dis_submit_u8: start, inputs uploaded, compute done, result copied
+  bool ev_valid = false;
   int launches = 0;
   bool in_flight = false;
 };
@@ -239,12 +240,17 @@ size_t carve(dis_handle* h, int w, int h_img, char* base, bool assign) {
   std::vector<LevelBufs> lv(q.lv_f + 1);
   uint8_t* d_a = c.take<uint8_t>((size_t)w * h_img * h->noc);
   uint8_t* d_b = c.take<uint8_t>((size_t)w * h_img * h->noc);
+  // the product path builds level lv_l straight from the u8 frames (enqueue_pyramids); the finer levels exist only
+  // when every level is built the reference's way (taps == 1, or lv_l > 8 where the block mean is no longer exact)
+  const bool fine_levels = h->taps == 1 || q.lv_l > 8;
   for (int l = 0; l <= q.lv_f; ++l) {
     LevelBufs& L = lv[l];
     derive_level(h->opt, wp, hp, q.patchsz, l, &L.g);
     const size_t n = (size_t)L.g.pitch * L.g.th;
-    L.Ia = c.take<float>(n);
-    L.Ib = c.take<float>(n);
+    if (l >= q.lv_l || fine_levels) {
+      L.Ia = c.take<float>(n);
+      L.Ib = c.take<float>(n);
+    }
     if (l >= q.lv_l) {
       L.Iax = c.take<float>(n);
       L.Iay = c.take<float>(n);
@@ -321,6 +327,19 @@ void drop_graph(dis_handle* h) {
 int plan(dis_handle* h, int w, int h_img) {
   if (w <= 0 || h_img <= 0) return fail(h, DIS_ERR_INVALID_ARG, "non-positive image size %dx%d", w, h_img);
   if (w == h->w_org && h_img == h->h_org && !h->lv.empty()) return DIS_OK;
+  {  // validate the geometry before anything is committed: a failed plan must not leave a usable-looking handle
+    int wp, hp, left, top;
+    dis_padded_size(w, h_img, h->P.lv_f, &wp, &hp, &left, &top);
+    LevelGeom gc{};
+    derive_level(h->opt, wp, hp, h->P.patchsz, h->P.lv_f, &gc);
+    // coarsest level must be large enough for the kernels (and for the reference itself)
+    if (gc.w < 2 || gc.h < 4) {
+      h->lv.clear();
+      h->w_org = h->h_org = 0;
+      drop_graph(h);
+      return fail(h, DIS_ERR_UNSUPPORTED, "coarsest level %dx%d too small (lv_f=%d)", gc.w, gc.h, h->P.lv_f);
+    }
+  }
   const size_t one = carve(h, w, h_img, nullptr, false);  // workspace of one pair (multiple of 256 bytes)
   const size_t need = one * (size_t)h->nb;
   if (need > h->slab_bytes) {  // grow the slab (sizes above the create-time maximum re-allocate)
@@ -343,10 +362,6 @@ int plan(dis_handle* h, int w, int h_img) {
   }
   // SOR hand-off tags/epoch start from a clean slate (stale bytes could alias a tag)
   CU(h, cudaMemsetAsync(h->slab, 0, h->slab_bytes, h->stream));
-  // coarsest level must be large enough for the kernels (and for the reference itself)
-  const LevelGeom& gc = h->lv[h->P.lv_f].g;
-  if (gc.w < 2 || gc.h < 4)
-    return fail(h, DIS_ERR_UNSUPPORTED, "coarsest level %dx%d too small (lv_f=%d)", gc.w, gc.h, h->P.lv_f);
   return DIS_OK;
 }
 
@@ -532,8 +547,6 @@ int enqueue_finish(dis_handle* h) {
   launch_finish(L.flow, L.g.w, L.g.h, h->P.lv_l, h->left, h->top, h->w_org, h->h_org, h->mailbox, h->nb, h->bstride,
                 h->stream);
   h->launches++;
-  if (const char* dbg = getenv("DIS_DEBUG_EXTRA_LAUNCHES"))  // experiment: cost of a kernel launch at throughput
-    for (int i = 0, n = atoi(dbg); i < n; ++i) launch_set_mailbox(h->mailbox + 1, nullptr, nullptr, nullptr, 0, h->stream);
   CU(h, cudaGetLastError());
   return DIS_OK;
 }
@@ -783,6 +796,8 @@ int dis_destroy(dis_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   drop_graph(h);
+  for (cudaEvent_t e : h->ev)
+    if (e) cudaEventDestroy(e);
   if (h->slab) cudaFree(h->slab);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -837,8 +852,17 @@ int dis_enable_stage_timing(dis_handle* h, int on) {
 
 int dis_enable_taps(dis_handle* h, int on) {
   if (!h) return DIS_ERR_INVALID_ARG;
+  const int was = h->taps;
   h->taps = on == 2 ? 2 : (on != 0);
   if (!on) h->tapdata.clear();
+  if ((was == 1) != (h->taps == 1) && !h->lv.empty()) {  // the fine pyramid levels exist only for taps == 1: re-plan
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    const int w = h->w_org, hh = h->h_org;
+    h->lv.clear();
+    h->w_org = h->h_org = 0;
+    return plan(h, w, hh);
+  }
   return DIS_OK;
 }
 
@@ -884,145 +908,6 @@ int dis_host_alloc(void** ptr, size_t bytes) {
 }
 int dis_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? DIS_OK : DIS_ERR_CUDA; }
 
-// ---- groups: n pairs per graph launch ---------------------------------------------------------------------
-// A pair is a chain of ~90 dependent launches, most of them latency-bound (SOR wavefronts, coarse levels), and
-// the device exposes at most 32 hardware work queues, so with one pair per stream about 32 chains are in flight
-// and throughput = 32 / chain latency, well before the SMs are full (tools/stage_cost2.py: one more SOR sweep
-// costs exactly its latency / 32).  A group records the runs of n handles as n parallel branches of ONE graph
-// (fork/join through events during capture) and launches it on the first member's stream: n times as many
-// chains per queue, same kernels, same results.
-struct dis_group {
-  std::vector<dis_handle*> m;
-  cudaGraphExec_t graph_exec = nullptr;
-  int graph_w = 0, graph_h = 0, graph_n = 0;
-  int device = 0;
-  std::string err;
-};
-
-namespace {
-int gfail(dis_group* g, int code, const char* fmt, ...) {
-  char buf[512];
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(buf, sizeof buf, fmt, ap);
-  va_end(ap);
-  if (g) g->err = buf;
-  g_create_error = buf;
-  return code;
-}
-#define CUGR(g, call)                                                                                   \
-  do {                                                                                                  \
-    cudaError_t e_ = (call);                                                                            \
-    if (e_ != cudaSuccess)                                                                              \
-      return gfail(g, DIS_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-  } while (0)
-}  // namespace
-
-int dis_group_create(const dis_params* params, int channels, int max_w, int max_h, int device, int n, dis_group** out) {
-  if (!out || n < 1 || n > 64) return gfail(nullptr, DIS_ERR_INVALID_ARG, "dis_group_create: bad argument");
-  *out = nullptr;
-  dis_group* g = new dis_group;
-  g->device = device;
-  for (int i = 0; i < n; ++i) {
-    dis_handle* h = nullptr;
-    const int rc = dis_create_c(params, channels, max_w, max_h, device, &h);
-    if (rc != DIS_OK) {
-      dis_group_destroy(g);
-      return rc;
-    }
-    g->m.push_back(h);
-  }
-  *out = g;
-  return DIS_OK;
-}
-
-void dis_group_destroy(dis_group* g) {
-  if (!g) return;
-  cudaSetDevice(g->device);
-  if (!g->m.empty()) cudaStreamSynchronize(g->m[0]->stream);
-  if (g->graph_exec) cudaGraphExecDestroy(g->graph_exec);
-  for (dis_handle* h : g->m) dis_destroy(h);
-  delete g;
-}
-
-int dis_group_size(const dis_group* g) { return g ? (int)g->m.size() : 0; }
-const char* dis_group_last_error(const dis_group* g) { return g ? g->err.c_str() : g_create_error.c_str(); }
-void* dis_group_stream(dis_group* g) { return g && !g->m.empty() ? g->m[0]->stream : nullptr; }
-
-int dis_group_submit_u8_device(dis_group* g, int n, const uint8_t* const* d_a, const uint8_t* const* d_b, int w,
-                               int h_img, int pitch, float* const* d_flow) {
-  if (!g || !d_a || !d_b || !d_flow || n < 1 || n > (int)g->m.size())
-    return gfail(g, DIS_ERR_INVALID_ARG, "dis_group_submit_u8_device: bad argument");
-  CUGR(g, cudaSetDevice(g->device));
-  cudaStream_t lead = g->m[0]->stream;
-  bool replanned = false;
-  for (int i = 0; i < n; ++i) {
-    dis_handle* h = g->m[i];
-    if (!d_a[i] || !d_b[i] || !d_flow[i] || pitch < w * h->noc) return gfail(g, DIS_ERR_INVALID_ARG, "bad pair %d", i);
-    if (h->taps || h->stage_timing || h->kprof_on) return gfail(g, DIS_ERR_UNSUPPORTED, "taps/profiling need single handles");
-    replanned |= !(w == h->w_org && h_img == h->h_org && !h->lv.empty());
-    const int rc = plan(h, w, h_img);
-    if (rc != DIS_OK) return gfail(g, rc, "%s", h->err.c_str());
-  }
-  if (replanned) {
-    for (int i = 0; i < n; ++i) CUGR(g, cudaStreamSynchronize(g->m[i]->stream));  // workspace memsets of plan()
-    if (g->graph_exec) {
-      cudaGraphExecDestroy(g->graph_exec);
-      g->graph_exec = nullptr;
-    }
-  }
-  for (int i = 0; i < n; ++i)
-    launch_set_mailbox(g->m[i]->mailbox, d_a[i], d_b[i], reinterpret_cast<float2*>(d_flow[i]), pitch, lead);
-  if (!(g->graph_exec && g->graph_w == w && g->graph_h == h_img && g->graph_n == n)) {
-    if (g->graph_exec) {
-      cudaGraphExecDestroy(g->graph_exec);
-      g->graph_exec = nullptr;
-    }
-    std::vector<cudaEvent_t> ev(n);
-    for (auto& e : ev) CUGR(g, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    CUGR(g, cudaStreamBeginCapture(lead, cudaStreamCaptureModeThreadLocal));
-    CUGR(g, cudaEventRecord(ev[0], lead));
-    for (int i = 1; i < n; ++i) CUGR(g, cudaStreamWaitEvent(g->m[i]->stream, ev[0], 0));  // fork
-    int rc = DIS_OK;
-    for (int i = 0; i < n && rc == DIS_OK; ++i) {
-      dis_handle* h = g->m[i];
-      h->launches = 1;
-      rc = enqueue_pyramids(h);
-      if (rc == DIS_OK) rc = enqueue_engine(h, nullptr);
-      if (rc == DIS_OK) rc = enqueue_finish(h);
-      h->tm.launches = h->launches;
-    }
-    for (int i = 1; i < n; ++i) {  // join
-      cudaEventRecord(ev[i], g->m[i]->stream);
-      cudaStreamWaitEvent(lead, ev[i], 0);
-    }
-    cudaGraph_t graph = nullptr;
-    const cudaError_t e = cudaStreamEndCapture(lead, &graph);
-    for (auto& x : ev) cudaEventDestroy(x);
-    if (rc != DIS_OK || e != cudaSuccess) {
-      if (graph) cudaGraphDestroy(graph);
-      return gfail(g, rc != DIS_OK ? rc : DIS_ERR_CUDA, "group capture failed: %s",
-                   rc != DIS_OK ? "enqueue error" : cudaGetErrorString(e));
-    }
-    const cudaError_t e2 = cudaGraphInstantiate(&g->graph_exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (e2 != cudaSuccess) return gfail(g, DIS_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e2));
-    g->graph_w = w;
-    g->graph_h = h_img;
-    g->graph_n = n;
-  }
-  CUGR(g, cudaGraphLaunch(g->graph_exec, lead));
-  return DIS_OK;
-}
-
-int dis_group_wait(dis_group* g) {
-  if (!g || g->m.empty()) return DIS_ERR_INVALID_ARG;
-  CUGR(g, cudaSetDevice(g->device));
-  CUGR(g, cudaStreamSynchronize(g->m[0]->stream));
-  CUGR(g, cudaGetLastError());
-  return DIS_OK;
-}
-
 int dis_submit_u8_device(dis_handle* h, const uint8_t* d_a, const uint8_t* d_b, int w, int h_img, int pitch,
                          float* d_flow) {
   if (!h || !d_a || !d_b || !d_flow || pitch < w * h->noc) return h ? fail(h, DIS_ERR_INVALID_ARG, "bad argument") : DIS_ERR_INVALID_ARG;
@@ -1058,10 +943,10 @@ int dis_submit_u8(dis_handle* h, const uint8_t* a, const uint8_t* b, int w, int 
   int rc = plan(h, w, h_img);
   if (rc != DIS_OK) return rc;
   reset_timings(h);
-  CU(h, cudaEventCreate(&h->ev[0]));
-  CU(h, cudaEventCreate(&h->ev[1]));
-  CU(h, cudaEventCreate(&h->ev[2]));
-  CU(h, cudaEventCreate(&h->ev[3]));
+  if (h->in_flight) return fail(h, DIS_ERR_INVALID_ARG, "a submission is already in flight on this handle: dis_wait() first");
+  for (int i = 0; i < 4; ++i)  // created once per handle, destroyed in dis_destroy
+    if (!h->ev[i]) CU(h, cudaEventCreate(&h->ev[i]));
+  h->ev_valid = false;
   CU(h, cudaEventRecord(h->ev[0], h->stream));
   const size_t rowb = (size_t)w * h->noc;
   CU(h, cudaMemcpy2DAsync(h->d_a, rowb, a, pitch, rowb, h_img, cudaMemcpyHostToDevice, h->stream));
@@ -1077,6 +962,7 @@ int dis_submit_u8(dis_handle* h, const uint8_t* a, const uint8_t* b, int w, int 
     CU(h, cudaMemcpyAsync(flow_out, h->d_out, sizeof(float2) * (size_t)w * h_img, cudaMemcpyDeviceToHost, h->stream));
   }
   CU(h, cudaEventRecord(h->ev[3], h->stream));
+  h->ev_valid = true;
   h->in_flight = true;
   return DIS_OK;
 }
@@ -1085,14 +971,11 @@ int dis_wait(dis_handle* h) {
   if (!h) return DIS_ERR_INVALID_ARG;
   CU(h, cudaSetDevice(h->device));
   CU(h, cudaStreamSynchronize(h->stream));
-  if (h->ev[0]) {
+  if (h->ev_valid) {
     cudaEventElapsedTime(&h->tm.h2d_ms, h->ev[0], h->ev[1]);
     cudaEventElapsedTime(&h->tm.d2h_ms, h->ev[2], h->ev[3]);
     cudaEventElapsedTime(&h->tm.total_ms, h->ev[0], h->ev[3]);
-    for (int i = 0; i < 4; ++i) {
-      cudaEventDestroy(h->ev[i]);
-      h->ev[i] = nullptr;
-    }
+    h->ev_valid = false;
     if (h->P.verbosity > 0)  // format of kroeger/oflow.cpp:359
       printf("TIME (O.Flow Run-Time   ) (ms): %3g\n", h->tm.total_ms - h->tm.h2d_ms - h->tm.d2h_ms);
   }
@@ -1115,6 +998,40 @@ int dis_fetch_level_flow(dis_handle* h, float* out, size_t n_floats) {
   CU(h, cudaSetDevice(h->device));
   CU(h, cudaMemcpyAsync(out, L.flow, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
+  return DIS_OK;
+}
+
+int dis_level_flow_size(const dis_handle* h, int* w_l, int* h_l) {
+  if (!h || h->lv.empty()) return DIS_ERR_INVALID_ARG;
+  const LevelBufs& L = h->lv[h->P.lv_l];
+  if (w_l) *w_l = L.g.w;
+  if (h_l) *h_l = L.g.h;
+  return DIS_OK;
+}
+
+const float* dis_level_flow_ptr(const dis_handle* h, int pair) {
+  if (!h || h->lv.empty() || pair < 0 || pair >= h->nb) return nullptr;
+  return reinterpret_cast<const float*>(bshift(h->lv[h->P.lv_l].flow, (size_t)pair * h->bstride));
+}
+
+int dis_copy_level_flow_device(dis_handle* h, int pair, float* d_dst) {
+  if (!h || !d_dst || h->lv.empty() || pair < 0 || pair >= h->nb)
+    return h ? fail(h, DIS_ERR_INVALID_ARG, "dis_copy_level_flow_device: bad argument") : DIS_ERR_INVALID_ARG;
+  const LevelBufs& L = h->lv[h->P.lv_l];
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaMemcpyAsync(d_dst, bshift(L.flow, (size_t)pair * h->bstride), sizeof(float2) * (size_t)L.g.w * L.g.h,
+                        cudaMemcpyDeviceToDevice, h->stream));
+  return DIS_OK;
+}
+
+int dis_copy_level_flows_device(dis_handle* h, int n_pairs, float* d_dst) {
+  if (!h || !d_dst || h->lv.empty() || n_pairs < 1 || n_pairs > h->nb)
+    return h ? fail(h, DIS_ERR_INVALID_ARG, "dis_copy_level_flows_device: bad argument") : DIS_ERR_INVALID_ARG;
+  const LevelBufs& L = h->lv[h->P.lv_l];
+  const size_t bytes = sizeof(float2) * (size_t)L.g.w * L.g.h;
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaMemcpy2DAsync(d_dst, bytes, L.flow, h->nb > 1 ? h->bstride : bytes, bytes, n_pairs, cudaMemcpyDeviceToDevice,
+                          h->stream));
   return DIS_OK;
 }
 

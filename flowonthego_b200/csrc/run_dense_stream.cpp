@@ -61,7 +61,8 @@ int main(int argc, char** argv) {
   const int verbosity = p.verbosity;
   p.verbosity = 0;  // per-pair TIME lines would interleave; a summary is printed instead
   dis_video* v = nullptr;
-  if (dis_video_create(&p, channels, first.w, first.h, 0, depth, &v) != DIS_OK) {
+  if (dis_video_create(&p, channels, first.w, first.h, 0, depth, &v) != DIS_OK ||
+      dis_video_set_output(v, DIS_VIDEO_OUT_FULL) != DIS_OK) {  // .flo files hold the full-resolution field
     fprintf(stderr, "run_dense_stream: %s\n", dis_last_error(nullptr));
     return 1;
   }

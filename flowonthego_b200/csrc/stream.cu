@@ -20,7 +20,9 @@
 
 struct dis_video {
   int w = 0, h = 0, noc = 1, device = 0, depth = 0;
-  size_t frame_bytes = 0, flow_floats = 0;
+  size_t frame_bytes = 0, flow_floats = 0;  // flow_floats: full-resolution field
+  int out_mode = DIS_VIDEO_OUT_LEVEL;
+  int lw = 0, lh = 0;                       // size of the level-lv_l flow (the engine's own output)
   std::vector<dis_handle*> eng;
   std::vector<uint8_t*> d_frame;       // ring, depth + 2 slots
   std::vector<cudaEvent_t> uploaded;   // per slot: upload finished
@@ -70,6 +72,7 @@ int dis_video_create(const dis_params* params, int channels, int w, int h, int d
     if (rc != DIS_OK) return bail(rc);
     v->eng.push_back(e);
   }
+  dis_level_flow_size(v->eng[0], &v->lw, &v->lh);
   if (cudaSetDevice(device) != cudaSuccess) return bail(DIS_ERR_CUDA);
   for (int i = 0; i < depth + 2; ++i) {
     uint8_t* p = nullptr;
@@ -106,6 +109,25 @@ void dis_video_destroy(dis_video* v) {
   for (cudaEvent_t e : v->done) cudaEventDestroy(e);
   delete v;
 }
+
+int dis_video_set_output(dis_video* v, int mode) {
+  if (!v || (mode != DIS_VIDEO_OUT_LEVEL && mode != DIS_VIDEO_OUT_FULL) || dis_video_pending(v) > 0) {
+    dis::set_global_error("dis_video_set_output: bad mode, or pairs in flight");
+    return DIS_ERR_INVALID_ARG;
+  }
+  v->out_mode = mode;
+  return DIS_OK;
+}
+
+size_t dis_video_flow_size(const dis_video* v, int* w_out, int* h_out) {
+  if (!v) return 0;
+  const bool lvl = v->out_mode == DIS_VIDEO_OUT_LEVEL;
+  if (w_out) *w_out = lvl ? v->lw : v->w;
+  if (h_out) *h_out = lvl ? v->lh : v->h;
+  return lvl ? (size_t)v->lw * v->lh * 2 : v->flow_floats;
+}
+
+dis_handle* dis_video_handle(dis_video* v, int k) { return (v && k >= 0 && k < v->depth) ? v->eng[k] : nullptr; }
 
 int dis_video_pending(const dis_video* v) { return v ? (int)((v->pushed > 0 ? v->pushed - 1 : 0) - v->popped) : 0; }
 
@@ -163,7 +185,12 @@ int dis_video_push(dis_video* v, const uint8_t* frame, int pitch, float* flow_ou
     dis::set_global_error("%s", dis_last_error(v->eng[k]));
     return rc;
   }
-  CUV(cudaMemcpyAsync(flow_out, v->d_flow[k], v->flow_floats * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (v->out_mode == DIS_VIDEO_OUT_LEVEL) {  // the engine's own output, straight from the handle's workspace
+    CUV(cudaMemcpyAsync(flow_out, dis_level_flow_ptr(v->eng[k], 0), (size_t)v->lw * v->lh * 2 * sizeof(float),
+                        cudaMemcpyDeviceToHost, st));
+  } else {
+    CUV(cudaMemcpyAsync(flow_out, v->d_flow[k], v->flow_floats * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
   v->host_out[k] = flow_out;
   return DIS_OK;
 }

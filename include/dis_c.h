@@ -155,6 +155,17 @@ int dis_submit_u8_device(dis_handle* h, const uint8_t* d_a, const uint8_t* d_b, 
 /* Raw engine output of the last run_u8 (level lv_l, padded size), for parity tests against the
  * reference's OFClass output before the OpenCV upsampling: (w_pad/2^lv_l)*(h_pad/2^lv_l)*2. */
 int dis_fetch_level_flow(dis_handle* h, float* out, size_t n_floats);
+/* Size of that output for the current plan: (w_pad/2^lv_l) x (h_pad/2^lv_l). */
+int dis_level_flow_size(const dis_handle* h, int* w_l, int* h_l);
+/* Device-to-device copy of the level-lv_l flow of pair `pair` (0 for a single-pair handle, < batch for a batched
+ * one) into d_dst (w_l*h_l*2 floats on the handle's device), enqueued on the handle's stream behind the run that
+ * produces it.  This is what a multi-GPU job gathers over NCCL: the engine's output stays in HBM. */
+int dis_copy_level_flow_device(dis_handle* h, int pair, float* d_dst);
+/* The same for pairs 0..n_pairs-1 of a batched handle in one strided copy: d_dst is [n_pairs][h_l][w_l][2]. */
+int dis_copy_level_flows_device(dis_handle* h, int n_pairs, float* d_dst);
+/* Device address of that flow inside the handle's workspace (valid until the next re-plan; rewritten by the
+ * handle's next run), or NULL. */
+const float* dis_level_flow_ptr(const dis_handle* h, int pair);
 
 /* CUDA stream of the handle as a cudaStream_t (void* here to keep CUDA out of the header). */
 void* dis_stream(dis_handle* h);
@@ -190,21 +201,6 @@ int dis_batch_size(const dis_handle* h);
 int dis_submit_u8_device_batch(dis_handle* h, int n_pairs, const uint8_t* const* d_a, const uint8_t* const* d_b, int w,
                                int h_img, int pitch, float* const* d_flow);
 
-/* ---- groups: several pairs per launch ----------------------------------------------------------------- */
-/* A group owns n engine handles and records their runs as n parallel branches of one CUDA graph, launched on one
- * stream: the device runs n times as many dependent kernel chains per hardware work queue.  Each
- * pair's result is bit-identical to dis_run_u8.  d_a / d_b / d_flow: arrays of n_pairs device pointers
- * (n_pairs <= n); all pairs share w, h and pitch.  Asynchronous; dis_group_wait() waits for all pairs. */
-typedef struct dis_group dis_group;
-int dis_group_create(const dis_params* params, int channels, int max_w, int max_h, int device, int n, dis_group** out);
-void dis_group_destroy(dis_group* g);
-int dis_group_size(const dis_group* g);
-int dis_group_submit_u8_device(dis_group* g, int n_pairs, const uint8_t* const* d_a, const uint8_t* const* d_b, int w,
-                               int h_img, int pitch, float* const* d_flow);
-int dis_group_wait(dis_group* g);
-void* dis_group_stream(dis_group* g);
-const char* dis_group_last_error(const dis_group* g);
-
 /* ---- video-stream front end ------------------------------------------------------------------ */
 /* Consecutive frames in, one flow field per consecutive pair out (the loop the reference's CUDA twin runs over a
  * video, src/main.cpp; kroeger/run_dense.cpp itself handles one pair per process).  `depth` pairs are in flight
@@ -216,6 +212,17 @@ const char* dis_group_last_error(const dis_group* g);
 typedef struct dis_video dis_video;
 int dis_video_create(const dis_params* params, int channels, int w, int h, int device, int depth, dis_video** out);
 void dis_video_destroy(dis_video* v);
+/* What dis_video_push copies back per pair.  DIS_VIDEO_OUT_LEVEL (the default for streams): the engine's own
+ * output as OFC::OFClass delivers it -- level lv_l, dis_video_flow_size() floats, 1.04 MB per 1080p pair at
+ * lv_l = 2 -- leaving the x2^lv_l resize + crop of kroeger/run_dense.cpp:407-414 to the consumer;
+ * DIS_VIDEO_OUT_FULL: the full-resolution w x h x 2 flow (what run_dense writes to the .flo file; 16.6 MB per
+ * 1080p pair).  The computation is the same either way.  Only while no pair is in flight. */
+typedef enum dis_video_output { DIS_VIDEO_OUT_LEVEL = 0, DIS_VIDEO_OUT_FULL = 1 } dis_video_output;
+int dis_video_set_output(dis_video* v, int mode);
+/* Floats per flow field handed back in the current output mode, and its width / height. */
+size_t dis_video_flow_size(const dis_video* v, int* w_out, int* h_out);
+/* k-th engine handle (0 <= k < depth) -- e.g. for dis_stream(); owned by the video object. */
+dis_handle* dis_video_handle(dis_video* v, int k);
 int dis_video_push(dis_video* v, const uint8_t* frame, int pitch, float* flow_out);
 int dis_video_pop(dis_video* v, float** flow_out);
 int dis_video_pending(const dis_video* v);

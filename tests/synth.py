@@ -52,3 +52,38 @@ def synth_pair_bgr(w, h, seed=0, **kw):
     a = np.stack([texture(w, h, seed * 3 + k + 100) for k in range(3)], -1)
     b = np.stack([warp(np.ascontiguousarray(a[..., k]), M) for k in range(3)], -1)
     return np.ascontiguousarray(a), np.ascontiguousarray(b), gt_flow(w, h, M)
+
+
+def c5_matrix(t, w, h):
+    """rotation 0.05 deg*t about the centre x scale 1+1e-4 t + shift (0.9t,-0.4t)."""
+    return affine(w, h, rot_deg=0.05 * t, scale=1.0 + 1e-4 * t, shift=(0.9 * t, -0.4 * t))
+
+
+def c5_frame(base, k):
+    """Frame k of the C5 stream: triangle-wave affine trajectory (period 128 frames) of `base`."""
+    h, w = base.shape[:2]
+    t = k % 64 if (k // 64) % 2 == 0 else 64 - (k % 64)
+    return warp(base, c5_matrix(t, w, h))
+
+
+def c5_frames(base, n_frames):
+    return np.stack([c5_frame(base, k) for k in range(n_frames)])
+
+
+def load_gray(name):
+    """Committed first frames (tests/golden/*.png, written by tests/golden/make_golden_full.py)."""
+    import cv2
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)
+    im = cv2.imread(path, cv2.IMREAD_GRAYSCALE)
+    if im is None:
+        raise FileNotFoundError(path)
+    return im
+
+
+def stream_frame(base, k, rot_deg, dscale, shift, period=64):
+    """Frame k of a triangle-wave affine trajectory: step t of the trajectory applies rotation rot_deg*t,
+    scale 1 + dscale*t and shift*t to `base` (c5_frame is stream_frame(base, k, 0.05, 1e-4, (0.9, -0.4)))."""
+    h, w = base.shape[:2]
+    t = k % period if (k // period) % 2 == 0 else period - (k % period)
+    return warp(base, affine(w, h, rot_deg=rot_deg * t, scale=1.0 + dscale * t, shift=(shift[0] * t, shift[1] * t)))

@@ -289,30 +289,6 @@ def test_many_sor_sweeps_and_inner_iterations():
         F.Engine(params(2, 1024, tv_solverit=300), 200, 140)
 
 
-def test_group_of_pairs_per_launch():
-    """dis_group_*: n pairs as parallel branches of one graph; every pair equals a separate run."""
-    import torch
-    w, h, n = 322, 198, 3
-    p = params(2, 1024, lv_f=3, lv_l=1)
-    pairs = [synth_pair(w, h, seed=30 + k)[:2] for k in range(n)]
-    da = [torch.from_numpy(x[0]).cuda() for x in pairs]
-    db = [torch.from_numpy(x[1]).cuda() for x in pairs]
-    out = torch.zeros((n, h, w, 2), dtype=torch.float32, device="cuda")
-    with F.EngineGroup(p, w, h, n) as g:
-        for rep in range(2):  # capture, then replay
-            out.zero_()
-            g.submit_u8_device([x.data_ptr() for x in da], [x.data_ptr() for x in db], w, h, w,
-                               [out[k].data_ptr() for k in range(n)])
-            g.wait()
-            for k in range(n):
-                assert bits_differ(out[k].cpu().numpy(), port.run_u8(pairs[k][0], pairs[k][1], p.to_dict())) == 0, (rep, k)
-        g.submit_u8_device([da[0].data_ptr()], [db[0].data_ptr()], w, h, w, [out[2].data_ptr()])  # fewer pairs
-        g.wait()
-        assert bits_differ(out[2].cpu().numpy(), out[0].cpu().numpy()) == 0
-        with pytest.raises(F.DisError):
-            g.submit_u8_device([0], [0], w, h, w, [0])
-
-
 @pytest.mark.parametrize("channels,usefbcon,batch", [(1, 0, 4), (1, 1, 3), (3, 0, 2)])
 def test_batched_handle(channels, usefbcon, batch):
     """dis_create_batch: every launch serves `batch` pairs; each pair equals a separate run, also with fewer pairs

@@ -33,13 +33,17 @@ def test_stream_equals_pairwise(channels, depth):
     w, h, n = 322, 198, 8
     frames = sequence(w, h, n, channels=channels)
     p = F.Params.preset(2, 1024, verbosity=0).copy(lv_f=3, lv_l=1)
-    with F.FlowStream(p, w, h, depth=depth, channels=channels) as s:
+    with F.FlowStream(p, w, h, depth=depth, channels=channels, output="full") as s:
         flows = list(s.flows(frames))
         assert s.pending == 0
-    assert len(flows) == n - 1
+    with F.FlowStream(p, w, h, depth=depth, channels=channels) as s:  # default: the engine's level-lv_l output
+        lflows = list(s.flows(frames))
+        assert s.flow_shape == (200 // 2, 328 // 2, 2)  # padded to a multiple of 2^lv_f = 8, level lv_l = 1
+    assert len(flows) == n - 1 and len(lflows) == n - 1
     with F.Engine(p, w, h, channels=channels) as e:
         for k in range(n - 1):
             assert bits_differ(flows[k], e.run_u8(frames[k], frames[k + 1])) == 0, k
+            assert bits_differ(lflows[k], e.level_flow(w, h)) == 0, k
     # and the oracle on one pair, so that this file stands on its own
     assert bits_differ(flows[2], port.run_u8(frames[2], frames[3], p.to_dict())) == 0
 
@@ -47,7 +51,7 @@ def test_stream_equals_pairwise(channels, depth):
 def test_stream_protocol_errors():
     p = F.Params.preset(2, 1024, verbosity=0).copy(lv_f=2, lv_l=1)
     fr = sequence(128, 96, 4)
-    with F.FlowStream(p, 128, 96, depth=2) as s:
+    with F.FlowStream(p, 128, 96, depth=2, output="full") as s:
         with pytest.raises(F.DisError):
             s.pop()                      # nothing in flight
         s.push(fr[0])
