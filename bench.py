@@ -250,6 +250,7 @@ class Bench:
         self.Sb = max(1, args.batch_handles or cfg["bh"] or 1)
         self.p = F.Params.from_argv(cfg["argv"].split())
         self.arith = args.arith
+        self.no_gather = args.no_gather
         self.main_stream = torch.cuda.current_stream()
 
     def barrier(self):
@@ -305,22 +306,36 @@ class Bench:
         d_frames = torch.from_numpy(frames).to(self.dev)
         d_out = torch.empty((nE, nb, H, W, 2), dtype=torch.float32, device=self.dev)
         fptr = [d_frames[i].data_ptr() for i in range(B + 1)]
+        optr = [[d_out[k, j].data_ptr() for j in range(nb)] for k in range(nE)]
         chunks = [list(range(c, min(c + nb, B))) for c in range(0, B, nb)]
         lshape = None
-        gather = self.dist is not None
+        gather = self.dist is not None and not self.no_gather
         turn = [0]
-        if gather:  # level flows of a step -> staging (D2D on the engine's stream) -> NCCL gather on rank 0, double-buffered
+        NBUF = 4
+        if gather:  # level flows of a step -> staging (D2D on the engine's stream) -> NCCL gather on rank 0; NBUF staging
+            # buffers, so a step only waits for the gather issued NBUF steps earlier (never for a recent one: a handle
+            # that idles until every rank has delivered the previous step costs ~9 % of the pairs/s)
             lshape = engines[0].level_flow_shape()
-            stage = [torch.zeros((B,) + lshape, dtype=torch.float32, device=self.dev) for _ in range(2)]
-            gl = [[torch.empty_like(stage[0]) for _ in range(self.world)] for _ in range(2)] if self.rank == 0 else [None, None]
+            stage = [torch.zeros((B,) + lshape, dtype=torch.float32, device=self.dev) for _ in range(NBUF)]
+            gl = [[torch.empty_like(stage[0]) for _ in range(self.world)] for _ in range(NBUF)] if self.rank == 0 else [None] * NBUF
+            sptr = [t.data_ptr() for t in stage]
+            lbytes = int(np.prod(lshape)) * 4
             gstream = torch.cuda.Stream(device=self.dev)
-            g_done = [None, None]
+            g_done = [None] * NBUF
             step_no = [0]
 
+        host_t = [0.0, 0]
+
         def step():
+            t_h0 = time.perf_counter()
+            step_inner()
+            host_t[0] += time.perf_counter() - t_h0
+            host_t[1] += 1
+
+        def step_inner():
             buf = None
             if gather:
-                buf = step_no[0] & 1
+                buf = step_no[0] % NBUF
                 step_no[0] += 1
             used = set()
             for idx in chunks:
@@ -330,15 +345,12 @@ class Bench:
                 if gather and g_done[buf] is not None and k not in used:
                     streams[k].wait_event(g_done[buf])  # staging buffer free again (gather of step-2 finished)
                 used.add(k)
+                if gather:  # the run's last kernel also writes the level flows into the staging buffer of this step
+                    e.set_level_export([sptr[buf] + i * lbytes for i in idx])
                 if nb > 1:
-                    e.submit_u8_device_batch([fptr[i] for i in idx], [fptr[i + 1] for i in idx], W, H, W,
-                                             [d_out[k, j].data_ptr() for j in range(len(idx))])
-                    if gather:
-                        e.copy_level_flows_device(len(idx), stage[buf][idx[0]].data_ptr())
+                    e.submit_u8_device_batch([fptr[i] for i in idx], [fptr[i + 1] for i in idx], W, H, W, optr[k][:len(idx)])
                 else:
-                    e.submit_u8_device(fptr[idx[0]], fptr[idx[0] + 1], W, H, W, d_out[k, 0].data_ptr())
-                    if gather:
-                        e.copy_level_flow_device(0, stage[buf][idx[0]].data_ptr())
+                    e.submit_u8_device(fptr[idx[0]], fptr[idx[0] + 1], W, H, W, optr[k][0])
             if gather:
                 for k in used:
                     ev = torch.cuda.Event()
@@ -362,15 +374,15 @@ class Bench:
         ms = self.timed(step, K, streams, tail)
         clocks = sampler.stop() if (self.rank == 0 and sample_clocks) else None
         launches_per_call = engines[0].timings()["launches"]
-        res = dict(ms=ms, value=self.world * B * K / (ms / 1e3), clocks=clocks, launches_per_call=launches_per_call,
+        res = dict(ms=ms, host_submit_ms_per_step=1e3 * host_t[0] / max(host_t[1], 1), value=self.world * B * K / (ms / 1e3), clocks=clocks, launches_per_call=launches_per_call,
                    calls_per_step=len(chunks), n_engines=nE,
                    gather=None if not gather else dict(
                        what="level-%d flows (%dx%d) of every step gathered on rank 0 with torch.distributed.gather over NCCL, "
-                            "overlapped with the next step's compute" % (self.p.lv_l, lshape[1], lshape[0]),
+                            "overlapped with the following steps' compute" % (self.p.lv_l, lshape[1], lshape[0]),
                        bytes_per_step_into_rank0=int(np.prod(lshape)) * 4 * B * (self.world - 1)))
         summ = None
         if gather and self.rank == 0:  # proof that the gathered fields are the computed ones
-            last = (step_no[0] - 1) & 1
+            last = (step_no[0] - 1) % NBUF
             self.torch.cuda.synchronize()
             summ = [float(gl[last][r].abs().mean()) for r in range(self.world)]
         res["gathered_mean_abs_flow_per_rank"] = summ
@@ -571,8 +583,15 @@ def main():
     ap.add_argument("--pairs-per-launch", type=int, default=None,
                     help="batched handles for the device-resident arm (dis_create_batch); 1 = one pair per launch")
     ap.add_argument("--batch-handles", type=int, default=0, help="number of batched handles per GPU")
+    ap.add_argument("--nccl-channels", type=int, default=0, help="NCCL_MAX_NCHANNELS for the result gather (default: by N)")
+    ap.add_argument("--no-gather", action="store_true", help="N > 1: leave the level flows on their GPUs (diagnostic)")
     ap.add_argument("--no-extra", action="store_true", help="skip the side measurements (4K, full-flow e2e, latency)")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: keep a private copy of it and send everything else that writes to fd 1
+    # (NCCL's version banner, library chatter) to stderr
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -616,7 +635,8 @@ def main():
                           "steps": Kr, "warmup": Wr, "ms_per_step": 1e3 * sum(walls) / len(walls),
                           "ms_per_pair": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                           "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": cb,
-                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}),
+              file=json_out, flush=True)
         return
 
     # ---------------------------------------------------------------- product arm (B200)
@@ -634,7 +654,9 @@ def main():
     bench = Bench(cfg, args, rank, local_rank, world)
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
+        # the only collective is the result gather (<= 1 GB per step into rank 0): a few channels move that easily
+        # and leave the SMs to the flow kernels
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", str(args.nccl_channels or max(2, min(8, N))))
         dist.init_process_group("nccl", device_id=bench.dev)
         bench.dist = dist
 
@@ -696,7 +718,7 @@ def main():
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
         line.update(extras)
-        print(json.dumps(line))
+        print(json.dumps(line), file=json_out, flush=True)
     if bench.dist is not None:
         bench.dist.barrier()
         bench.dist.destroy_process_group()

@@ -138,7 +138,7 @@ def lib():
         L.dis_video_handle.restype = vp
         L.dis_level_flow_size.argtypes = [vp, ctypes.POINTER(ip), ctypes.POINTER(ip)]
         L.dis_copy_level_flow_device.argtypes = [vp, ip, vp]
-        L.dis_copy_level_flows_device.argtypes = [vp, ip, vp]
+        L.dis_set_level_export.argtypes = [vp, ip, ctypes.POINTER(vp)]
         L.dis_level_flow_ptr.argtypes = [vp, ip]
         L.dis_level_flow_ptr.restype = vp
         L.dis_flow_to_color.argtypes = [fp, ip, ip, ctypes.c_float, ip, vp, fp]
@@ -292,9 +292,11 @@ class Engine:
         """Enqueue a device-to-device copy of the level flow of `pair` to device pointer d_dst on the engine's stream."""
         _check(lib().dis_copy_level_flow_device(self._h, int(pair), d_dst), self._h)
 
-    def copy_level_flows_device(self, n_pairs, d_dst):
-        """Batched handle: level flows of pairs 0..n_pairs-1 -> contiguous [n_pairs][h_l][w_l][2] at d_dst."""
-        _check(lib().dis_copy_level_flows_device(self._h, int(n_pairs), d_dst), self._h)
+    def set_level_export(self, d_level):
+        """The following device submits also write pair b's level-lv_l flow to device pointer d_level[b]
+        (dis_set_level_export; [] turns it off)."""
+        arr = (ctypes.c_void_p * max(len(d_level), 1))(*d_level)
+        _check(lib().dis_set_level_export(self._h, len(d_level), arr), self._h)
 
     def level_flow(self, w, h):
         """Raw engine output (level lv_l, padded size) of the last run_u8."""

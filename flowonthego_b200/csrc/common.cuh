@@ -65,14 +65,15 @@ struct Mailbox {
   const uint8_t* a;
   const uint8_t* b;
   float2* out;
+  float2* lvl_out;  // optional: the finish kernel also copies the level-lv_l flow (the engine's own output) here
   int pitch;  // row pitch of a and b in bytes
 };
-void launch_set_mailbox(Mailbox* mb, const uint8_t* a, const uint8_t* b, float2* out, int pitch, cudaStream_t st);
 constexpr int kMaxBatch = 8;
 struct MailboxBatch {  // by-value kernel argument: the per-run pointers of up to kMaxBatch pairs
   const uint8_t* a[kMaxBatch];
   const uint8_t* b[kMaxBatch];
   float2* out[kMaxBatch];
+  float2* lvl[kMaxBatch];
 };
 void launch_set_mailboxes(Mailbox* mb0, size_t bstride, int nb, const MailboxBatch& m, int pitch, cudaStream_t st);
 

@@ -8,6 +8,18 @@
 namespace dis {
 namespace {
 
+// Optional export of the engine's own output (OFC::OFClass outflow = the level-lv_l flow the finish kernel reads)
+// to the per-run pointer in the mailbox: what a stream consumer or a multi-GPU result gather takes instead of the
+// full-resolution field.  Folded into the finish kernels: a separate copy after the graph costs ~70 us of
+// throughput per launch (measured), this costs one float2 per thread.
+__device__ __forceinline__ void export_level(const float2* __restrict__ fl, int n_px, const Mailbox* __restrict__ mb) {
+  float2* __restrict__ lo = mb->lvl_out;
+  if (lo == nullptr) return;
+  const int nthr = gridDim.x * gridDim.y * blockDim.x * blockDim.y;
+  const int tid = (blockIdx.y * gridDim.x + blockIdx.x) * (blockDim.x * blockDim.y) + threadIdx.y * blockDim.x + threadIdx.x;
+  for (int i = tid; i < n_px; i += nthr) lo[i] = fl[i];
+}
+
 // One thread = 4 consecutive output pixels of a row: the vertical weights and row pointers are shared, the four
 // source taps of each pixel come from L1.  Same expressions, in the same order, as a per-pixel evaluation.
 __global__ void __launch_bounds__(256) k_finish(const float2* __restrict__ fl, int wl, int hl, int lv_l,
@@ -16,6 +28,7 @@ __global__ void __launch_bounds__(256) k_finish(const float2* __restrict__ fl, i
   fl = bshift(fl, (size_t)blockIdx.z * bstride);  // blockIdx.z = pair of a batched handle
   mb = bshift(mb, (size_t)blockIdx.z * bstride);
   float2* __restrict__ out = mb->out;
+  export_level(fl, wl * hl, mb);
   const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x0 >= w_org || y >= h_org) return;
@@ -75,6 +88,7 @@ __global__ void __launch_bounds__(256) k_finish_x4(const float2* __restrict__ fl
   fl = bshift(fl, (size_t)blockIdx.z * bstride);  // blockIdx.z = pair of a batched handle
   mb = bshift(mb, (size_t)blockIdx.z * bstride);
   float2* __restrict__ out = mb->out;
+  export_level(fl, wl * hl, mb);
   const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y * blockDim.y + threadIdx.y;
   const int x0 = bx * 4, y0 = by * 4;
   if (x0 >= w_org || y0 >= h_org) return;

@@ -158,17 +158,6 @@ void launch(Src sa, Src sb, const LevelGeom& g, float* Ia, float* Iax, float* Ia
 
 }  // namespace
 
-__global__ void k_set_mailbox(Mailbox* mb, const uint8_t* a, const uint8_t* b, float2* out, int pitch) {
-  mb->a = a;
-  mb->b = b;
-  mb->out = out;
-  mb->pitch = pitch;
-}
-
-void launch_set_mailbox(Mailbox* mb, const uint8_t* a, const uint8_t* b, float2* out, int pitch, cudaStream_t st) {
-  k_set_mailbox<<<1, 1, 0, st>>>(mb, a, b, out, pitch);
-}
-
 __global__ void k_set_mailboxes(Mailbox* mb0, size_t bstride, int nb, const MailboxBatch m, int pitch) {
   const int b = threadIdx.x;
   if (b >= nb) return;
@@ -176,6 +165,7 @@ __global__ void k_set_mailboxes(Mailbox* mb0, size_t bstride, int nb, const Mail
   mb->a = m.a[b];
   mb->b = m.b[b];
   mb->out = m.out[b];
+  mb->lvl_out = m.lvl[b];
   mb->pitch = pitch;
 }
 

@@ -161,8 +161,10 @@ int dis_level_flow_size(const dis_handle* h, int* w_l, int* h_l);
  * one) into d_dst (w_l*h_l*2 floats on the handle's device), enqueued on the handle's stream behind the run that
  * produces it.  This is what a multi-GPU job gathers over NCCL: the engine's output stays in HBM. */
 int dis_copy_level_flow_device(dis_handle* h, int pair, float* d_dst);
-/* The same for pairs 0..n_pairs-1 of a batched handle in one strided copy: d_dst is [n_pairs][h_l][w_l][2]. */
-int dis_copy_level_flows_device(dis_handle* h, int n_pairs, float* d_dst);
+/* Export without an extra launch: the following dis_submit_u8_device[_batch] calls on this handle also write the
+ * level-lv_l flow of pair b to d_level[b] (device, w_l*h_l*2 floats each; done by the final kernel of the run).
+ * Stays in force until changed; n_pairs = 0 turns it off. */
+int dis_set_level_export(dis_handle* h, int n_pairs, float* const* d_level);
 /* Device address of that flow inside the handle's workspace (valid until the next re-plan; rewritten by the
  * handle's next run), or NULL. */
 const float* dis_level_flow_ptr(const dis_handle* h, int pair);

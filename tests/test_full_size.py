@@ -112,10 +112,22 @@ def test_gpu_c5_stream_batched_and_video():
     d = [torch.from_numpy(f).cuda() for f in frames]
     out = torch.empty((2, 1080, 1920, 2), dtype=torch.float32, device="cuda")
     with F.Engine(p, 1920, 1080, batch=2) as e:
-        e.submit_u8_device_batch([d[0].data_ptr(), d[1].data_ptr()], [d[1].data_ptr(), d[2].data_ptr()], 1920, 1080, 1920,
-                                 [out[0].data_ptr(), out[1].data_ptr()])
-        stage = torch.empty((2,) + e.level_flow_shape(), dtype=torch.float32, device="cuda")
-        e.copy_level_flows_device(2, stage.data_ptr())
+        stage = torch.zeros((2,) + e.level_flow_shape(), dtype=torch.float32, device="cuda")
+        e.set_level_export([stage[0].data_ptr(), stage[1].data_ptr()])  # what bench.py hands to the NCCL gather
+        for rep in range(2):  # capture, then graph replay
+            stage.zero_()
+            torch.cuda.synchronize()
+            e.submit_u8_device_batch([d[0].data_ptr(), d[1].data_ptr()], [d[1].data_ptr(), d[2].data_ptr()], 1920, 1080, 1920,
+                                     [out[0].data_ptr(), out[1].data_ptr()])
+            e.wait()
+            for k in (0, 1):
+                check(stage[k].cpu().numpy(), digs[k], "batched c5_%d" % k)
+        e.set_level_export([])
+        stage.zero_()
+        torch.cuda.synchronize()
+        e.submit_u8_device_batch([d[0].data_ptr()], [d[1].data_ptr()], 1920, 1080, 1920, [out[0].data_ptr()])
         e.wait()
-        for k in (0, 1):
-            check(stage[k].cpu().numpy(), digs[k], "batched c5_%d" % k)
+        assert float(stage.abs().max()) == 0.0
+        e.copy_level_flow_device(0, stage[1].data_ptr())
+        e.wait()
+        check(stage[1].cpu().numpy(), digs[0], "copy_level_flow_device")
