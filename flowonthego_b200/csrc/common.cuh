@@ -100,6 +100,10 @@ struct PatchSearchArgs {
 int launch_patch_search(const PatchSearchArgs& a, cudaStream_t st);
 void patch_search_init_device();
 void varref_init_device();
+// tolerance mode (DIS_OPT_ARITH = 1): the same sources compiled with FMA contraction allowed
+int launch_patch_search_fast(const PatchSearchArgs& a, cudaStream_t st);
+void patch_search_init_device_fast();
+void varref_init_device_fast();
 // densify.cu
 struct DensifyArgs {
   LevelGeom g;
@@ -124,6 +128,8 @@ struct VarRefBuffers {
 };
 int launch_varref(const LevelGeom& g, const VarParams& v, const float* I0, const float* I1,
                   float2* flow, const VarRefBuffers& b, cudaStream_t st, Prof* prof = nullptr);
+int launch_varref_fast(const LevelGeom& g, const VarParams& v, const float* I0, const float* I1,
+                       float2* flow, const VarRefBuffers& b, cudaStream_t st, Prof* prof = nullptr);
 void varref_sizes(int w, int h, int n_solver, size_t* n_coef4, size_t* n_du4, size_t* n_prog);
 // engine.cu: error text returned by dis_last_error(NULL) (handle-less entry points)
 void set_global_error(const char* fmt, ...);

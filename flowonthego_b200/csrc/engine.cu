@@ -116,6 +116,7 @@ struct dis_handle {
   bool use_graph = true;
   int sor_group = 0;  // DIS_OPT_SOR_GROUP: 0 auto, 8, 16
   bool level_output = false;  // DIS_OPT_LEVEL_OUTPUT
+  bool arith_fast = false;    // DIS_OPT_ARITH
   float2* lvl_export[kMaxBatch] = {};  // dis_set_level_export: per pair, device target of the level-lv_l flow (or null)
   int nb = 1;            // pairs per launch (dis_create_batch)
   size_t bstride = 0;    // bytes between the workspaces of consecutive pairs of the batch
@@ -477,6 +478,11 @@ int enqueue_engine(dis_handle* h, const float2* d_initflow) {
     vp.sor_group = h->sor_group ? h->sor_group : ((size_t)gfin.w * gfin.h >= (1u << 20) ? 16 : 8);
   }
   Prof* prof = h->kprof_on ? &h->kprof : nullptr;
+  // Tolerance mode: FMA-contracted builds of the search and the refinement.  Rounding differences grow with the
+  // number of Gauss-Newton iterations (2e-3 px at 16, 0.25 px at 128), so it is refused beyond 32.
+  const bool fast = h->arith_fast;
+  if (fast && q.maxiter > 32)
+    return fail(h, DIS_ERR_UNSUPPORTED, "DIS_OPT_ARITH = 1 (tolerance mode) is limited to maxiter <= 32 (got %d)", q.maxiter);
   for (int sl = q.lv_f; sl >= q.lv_l; --sl) {
     LevelBufs& L = h->lv[sl];
     float t_search = 0, t_dens = 0, t_var = 0;
@@ -492,7 +498,7 @@ int enqueue_engine(dis_handle* h, const float2* d_initflow) {
       const double np_ = (double)L.g.tw * L.g.th;
       ProfScope ps(prof, "k_patch_search", sl,
                    16.0 * np_ + (sl < q.lv_f ? 8.0 * (double)(L.g.w / 2) * (L.g.h / 2) : 0.0) + 16.0 * L.g.nop);
-      if (launch_patch_search(pa, h->stream)) return fail(h, DIS_ERR_UNSUPPORTED, "patch size %d", h->opt.p);
+      if ((fast ? launch_patch_search_fast : launch_patch_search)(pa, h->stream)) return fail(h, DIS_ERR_UNSUPPORTED, "patch size %d", h->opt.p);
       h->launches++;
       t_search = ck.stop();
     }
@@ -504,7 +510,7 @@ int enqueue_engine(dis_handle* h, const float2* d_initflow) {
       const double np_ = (double)L.g.tw * L.g.th;
       ProfScope ps(prof, "k_patch_search", sl,
                    16.0 * np_ + (sl < q.lv_f ? 8.0 * (double)(L.g.w / 2) * (L.g.h / 2) : 0.0) + 16.0 * L.g.nop);
-      if (launch_patch_search(pb, h->stream)) return fail(h, DIS_ERR_UNSUPPORTED, "patch size %d", h->opt.p);
+      if ((fast ? launch_patch_search_fast : launch_patch_search)(pb, h->stream)) return fail(h, DIS_ERR_UNSUPPORTED, "patch size %d", h->opt.p);
       h->launches++;
       t_search += ck.stop();
     }
@@ -529,13 +535,13 @@ int enqueue_engine(dis_handle* h, const float2* d_initflow) {
     if (q.usetvref) {
       StageClock ck(h, &h->tm.varref_ms);
       vp.n_inner = q.tv_innerit * (sl + 1);  // refine_variational.cpp:36
-      int n = launch_varref(L.g, vp, L.Ia, L.Ib, L.flow, h->vb, h->stream, prof);
+      int n = (fast ? launch_varref_fast : launch_varref)(L.g, vp, L.Ia, L.Ib, L.flow, h->vb, h->stream, prof);
       if (n < 0)
         return fail(h, DIS_ERR_UNSUPPORTED, "refinement of level %d (%dx%d, %d sweeps): need width >= 2, height >= 4, 1..256 sweeps",
                     sl, L.g.w, L.g.h, vp.n_solver);
       h->launches += n;
       if (fb && sl > q.lv_l) {  // oflow.cpp:291-294
-        n = launch_varref(L.g, vp, L.Ib, L.Ia, L.flow_bw, h->vb, h->stream, prof);
+        n = (fast ? launch_varref_fast : launch_varref)(L.g, vp, L.Ib, L.Ia, L.flow_bw, h->vb, h->stream, prof);
         h->launches += n;
       }
       t_var = ck.stop();
@@ -812,8 +818,10 @@ int dis_create_batch(const dis_params* params, int channels, int max_w, int max_
     return DIS_ERR_CUDA;
   }
   patch_search_init_device();
+  patch_search_init_device_fast();
   flowviz_init_device();
   varref_init_device();
+  varref_init_device_fast();
   rc = plan(h, max_w, max_h);
   if (rc != DIS_OK) {
     g_create_error = h->err;
@@ -854,6 +862,15 @@ int dis_set_option(dis_handle* h, int option, int value) {
       return DIS_OK;
     case DIS_OPT_USE_GRAPH:
       h->use_graph = value != 0;
+      return DIS_OK;
+    case DIS_OPT_ARITH:
+      if (value != 0 && value != 1) return fail(h, DIS_ERR_INVALID_ARG, "DIS_OPT_ARITH must be 0 (exact) or 1 (fast)");
+      if ((value != 0) != h->arith_fast) {
+        CU(h, cudaSetDevice(h->device));
+        CU(h, cudaStreamSynchronize(h->stream));
+        drop_graph(h);
+        h->arith_fast = value != 0;
+      }
       return DIS_OK;
     default:
       return fail(h, DIS_ERR_INVALID_ARG, "unknown option %d", option);

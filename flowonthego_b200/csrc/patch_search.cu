@@ -16,6 +16,14 @@
 // taps per element of the target image.  No FMA (-fmad=false), IEEE div/sqrt.
 #include "common.cuh"
 
+// This file is compiled twice (csrc/Makefile): with -fmad=false for the exact engine (the arithmetic contract of
+// common.cuh) and, as patch_search_fast.o with -fmad=true -DDIS_ARITH_FAST, for the opt-in tolerance mode
+// DIS_OPT_ARITH = 1: same code, same reduction order, but ptxas may contract a*b+c into FMA.
+#ifdef DIS_ARITH_FAST
+#define launch_patch_search launch_patch_search_fast
+#define patch_search_init_device patch_search_init_device_fast
+#endif
+
 namespace dis {
 namespace {
 

@@ -35,6 +35,13 @@
 
 #include "common.cuh"
 
+// Compiled twice like patch_search.cu: varref_fast.o (-fmad=true -DDIS_ARITH_FAST) serves DIS_OPT_ARITH = 1.
+#ifdef DIS_ARITH_FAST
+#define launch_varref launch_varref_fast
+#define varref_init_device varref_init_device_fast
+#define varref_sizes varref_sizes_fast
+#endif
+
 namespace dis {
 namespace {
 

@@ -102,7 +102,7 @@ int dis_create_c(const dis_params* params, int channels, int max_w, int max_h, i
 int dis_destroy(dis_handle* h);
 /* Replaces the parameter set (workspace is re-planned; fails if it no longer fits). */
 int dis_set_params(dis_handle* h, const dis_params* params);
-/* Execution options; none of them changes results.
+/* Execution options; none of the first three changes results.
  *   DIS_OPT_SOR_GROUP  8: smaller shared-memory footprint of the SOR wavefront kernel, best pairs/s when many
  *                      handles share the GPU; 16: lowest latency for a lone pair (about 7 % at 1080p); 0 (default):
  *                      16 when the finest processed level has >= 2^20 pixels (it fills the GPU alone), else 8.
@@ -110,8 +110,16 @@ int dis_set_params(dis_handle* h, const dis_params* params);
  * DIS_OPT_LEVEL_OUTPUT changes WHAT dis_run_u8 / dis_submit_u8 copy back, not how it is computed: 1 = the engine's
  * own output as the OFC::OFClass constructor delivers it (level lv_l, (w_pad/2^lv_l) x (h_pad/2^lv_l) x 2 floats,
  * see dis_padded_size), leaving the x2^lv_l resize and crop of kroeger/run_dense.cpp:407-414 to the caller -- 16x
- * less device-to-host traffic at lv_l = 2; 0 (default) = full-resolution flow. */
-typedef enum dis_option { DIS_OPT_SOR_GROUP = 1, DIS_OPT_USE_GRAPH = 2, DIS_OPT_LEVEL_OUTPUT = 3 } dis_option;
+ * less device-to-host traffic at lv_l = 2; 0 (default) = full-resolution flow.
+ *
+ * DIS_OPT_ARITH is the one option that DOES change results: 0 (default) = the exact engine, bit-identical to the
+ * reference's -msse4 build (no FMA contraction, reference reduction order); 1 = tolerance mode: the inverse search
+ * and the refinement kernels compiled with FMA contraction allowed (same reduction order).  Its output stays within
+ * the stated tolerance of the reference (mean |dflow| <= 1e-3 px, max <= 1e-2 px outside the border margin) for
+ * operating points with maxiter <= 32, which is enforced: a run with more iterations fails with
+ * DIS_ERR_UNSUPPORTED (rounding differences grow with the iteration count, 0.25 px at 128).  It is never part of a
+ * parity claim; bench.py reports it as a separate line (--arith fast). */
+typedef enum dis_option { DIS_OPT_SOR_GROUP = 1, DIS_OPT_USE_GRAPH = 2, DIS_OPT_LEVEL_OUTPUT = 3, DIS_OPT_ARITH = 4 } dis_option;
 int dis_set_option(dis_handle* h, int option, int value);
 /* Last error text of this handle (or of dis_create when h is NULL). Never NULL. */
 const char* dis_last_error(const dis_handle* h);

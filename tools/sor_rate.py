@@ -17,7 +17,7 @@ def sor_ms(w, h, T, grp):
         for _ in range(n): e.run_u8(a, b)
         ms = sum(r["ms"] for r in e.kernel_profile() if r["name"] == "k_sor_wavefront") / n
     return ms
-for grp in (8, 16):
+for grp in [int(x) for x in sys.argv[1:]] or (8, 16):
     base = None
     for (w, h, T) in ((480, 32, 1), (960, 32, 1), (480, 64, 1), (480, 32, 2), (480, 32, 3), (480, 96, 1), (480, 288, 1), (480, 288, 3)):
         ms = sor_ms(w, h, T, grp)
