@@ -132,6 +132,8 @@ def lib():
         L.dis_video_pop.argtypes = [vp, ctypes.POINTER(fp)]
         L.dis_video_pending.argtypes = [vp]
         L.dis_video_set_output.argtypes = [vp, ip]
+        L.dis_video_set_reuse.argtypes = [vp, ip]
+        L.dis_video_reuse.argtypes = [vp]
         L.dis_video_flow_size.argtypes = [vp, ctypes.POINTER(ip), ctypes.POINTER(ip)]
         L.dis_video_flow_size.restype = ctypes.c_size_t
         L.dis_video_handle.argtypes = [vp, ip]
@@ -375,7 +377,7 @@ class FlowStream:
     Engine.level_flow() of that pair bit for bit; output="full": the full-resolution (h, w, 2) field, equal to
     Engine.run_u8 on that pair bit for bit."""
 
-    def __init__(self, params, w, h, depth=8, device=0, channels=1, output="level"):
+    def __init__(self, params, w, h, depth=8, device=0, channels=1, output="level", reuse=None):
         self._v = ctypes.c_void_p()
         self.params = params if isinstance(params, Params) else Params.from_dict(params)
         self.w, self.h, self.depth, self.channels = int(w), int(h), int(depth), int(channels)
@@ -385,6 +387,9 @@ class FlowStream:
         self._frames = [pinned_empty(shape, np.uint8) for _ in range(self.depth + 1)]
         if output not in ("level", "full"):
             raise ValueError("output must be 'level' or 'full'")
+        if reuse is not None:  # pyramid reuse between consecutive pairs (default: on for 2 <= depth <= 8)
+            _check(lib().dis_video_set_reuse(self._v, int(bool(reuse))), None)
+        self.reuse = bool(lib().dis_video_reuse(self._v))
         _check(lib().dis_video_set_output(self._v, 0 if output == "level" else 1), None)
         fw, fh = ctypes.c_int(), ctypes.c_int()
         lib().dis_video_flow_size(self._v, ctypes.byref(fw), ctypes.byref(fh))

@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+struct dis_handle;
+
 namespace dis {
 
 // Geometry of one pyramid level (reference: camparam, kroeger/oflow.h:16-29; grid geometry
@@ -81,13 +83,13 @@ void launch_set_mailboxes(Mailbox* mb0, size_t bstride, int nb, const MailboxBat
 // pyramid.cu
 void launch_level0(const Mailbox* mb, int w_org, int h_org,
                    int left, int top, const LevelGeom& g, float* Ia, float* Iax, float* Iay,
-                   float* Ib, float* Ibx, float* Iby, cudaStream_t st);
+                   float* Ib, float* Ibx, float* Iby, cudaStream_t st, int only_b = 0);
 void launch_first_level(const Mailbox* mb, int L, int w_org, int h_org, int left, int top, const LevelGeom& g,
                         float* bm_a, float* bm_b, float* Ia, float* Iax, float* Iay, float* Ib, float* Ibx, float* Iby,
-                        cudaStream_t st);
+                        cudaStream_t st, int only_b = 0);
 void launch_downsample(const LevelGeom& gf, const LevelGeom& gc, const float* Ia_f, const float* Ib_f,
                        float* Ia, float* Iax, float* Iay, float* Ib, float* Ibx, float* Iby,
-                       cudaStream_t st);
+                       cudaStream_t st, int only_b = 0);
 // patch_search.cu
 struct PatchSearchArgs {
   const float *I0, *I0x, *I0y, *I1;
@@ -133,6 +135,13 @@ int launch_varref_fast(const LevelGeom& g, const VarParams& v, const float* I0, 
 void varref_sizes(int w, int h, int n_solver, size_t* n_coef4, size_t* n_du4, size_t* n_prog);
 // engine.cu: error text returned by dis_last_error(NULL) (handle-less entry points)
 void set_global_error(const char* fmt, ...);
+// engine.cu, for the video front end (stream.cu): pyramid reuse between consecutive pairs of a stream.  A chained
+// handle keeps the gradients of its second frame; with `reuse` set, its next run takes the first frame's pyramid from
+// `prev`'s second-frame buffers instead of building it (only_b launches), and every run records `pyramid_event` after
+// its pyramid kernels (inside the CUDA graph, as an external event-record node).
+int engine_chain(dis_handle* h, dis_handle* prev);
+void engine_set_reuse(dis_handle* h, bool reuse);
+cudaEvent_t engine_pyramid_event(dis_handle* h);
 // flowviz.cu
 void flowviz_init_device();
 void launch_flow_color(const float2* d_flow, int w, int h, float maxmotion, uint8_t* d_bgr, unsigned* d_stats,

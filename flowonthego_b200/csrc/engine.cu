@@ -120,11 +120,17 @@ struct dis_handle {
   float2* lvl_export[kMaxBatch] = {};  // dis_set_level_export: per pair, device target of the level-lv_l flow (or null)
   int nb = 1;            // pairs per launch (dis_create_batch)
   size_t bstride = 0;    // bytes between the workspaces of consecutive pairs of the batch
-  cudaGraphExec_t graph_exec = nullptr;
-  cudaGraph_t graph = nullptr;         // the captured graph (owns mb_node)
-  cudaGraphNode_t mb_node = nullptr;   // root node: k_set_mailboxes, re-parameterised before every launch
-  cudaKernelNodeParams mb_params{};
+  // two recorded variants: [0] both pyramids built, [1] first frame's pyramid reused from `chain_prev` (streams)
+  cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
+  cudaGraph_t graph[2] = {nullptr, nullptr};          // the captured graphs (own mb_node)
+  cudaGraphNode_t mb_node[2] = {nullptr, nullptr};    // root node: k_set_mailboxes, re-parameterised before every launch
+  cudaKernelNodeParams mb_params[2] = {};
   int graph_w = 0, graph_h = 0;
+  // pyramid reuse in a stream (engine_chain): see common.cuh
+  dis_handle* chain_prev = nullptr;
+  bool chained = false;      // keeps the gradients of the second frame
+  bool reuse_a = false;      // the next run takes frame a's pyramid from chain_prev
+  cudaEvent_t pyr_ev = nullptr;
 
   // timing / taps
   bool stage_timing = false;
@@ -157,6 +163,7 @@ int fail(dis_handle* h, int code, const char* fmt, ...) {
 }  // namespace
 
 namespace dis {
+int engine_chain(dis_handle* h, dis_handle* prev);
 void set_global_error(const char* fmt, ...) {
   char buf[512];
   va_list ap;
@@ -259,7 +266,7 @@ size_t carve(dis_handle* h, int w, int h_img, char* base, bool assign) {
     if (l >= q.lv_l) {
       L.Iax = c.take<float>(n);
       L.Iay = c.take<float>(n);
-      if (q.usefbcon) {
+      if (q.usefbcon || h->chained) {  // chained: this pair's second frame is the next pair's first
         L.Ibx = c.take<float>(n);
         L.Iby = c.take<float>(n);
       }
@@ -323,15 +330,17 @@ size_t carve(dis_handle* h, int w, int h_img, char* base, bool assign) {
 }
 
 void drop_graph(dis_handle* h) {
-  if (h->graph_exec) {
-    cudaGraphExecDestroy(h->graph_exec);
-    h->graph_exec = nullptr;
+  for (int v = 0; v < 2; ++v) {
+    if (h->graph_exec[v]) {
+      cudaGraphExecDestroy(h->graph_exec[v]);
+      h->graph_exec[v] = nullptr;
+    }
+    if (h->graph[v]) {
+      cudaGraphDestroy(h->graph[v]);
+      h->graph[v] = nullptr;
+    }
+    h->mb_node[v] = nullptr;
   }
-  if (h->graph) {
-    cudaGraphDestroy(h->graph);
-    h->graph = nullptr;
-  }
-  h->mb_node = nullptr;
 }
 
 int plan(dis_handle* h, int w, int h_img) {
@@ -403,6 +412,7 @@ int enqueue_pyramids(dis_handle* h) {
   // processed level is built straight from the u8 frames (bit-identical, see k_block_mean) and the finer levels are
   // not materialised.  With taps enabled (tests) every level is built the reference's way so that it can be compared.
   const int first = (h->taps == 1 || q.lv_l > 8) ? 0 : q.lv_l;
+  const int only_b = h->reuse_a ? 1 : 0;  // frame a's pyramid lives in chain_prev's second-frame buffers
   for (int l = first; l <= q.lv_f; ++l) {
     LevelBufs& L = h->lv[l];
     // SURVEY 8(d) B_P: u8 in (level 0 only), I of both frames out, Ix/Iy of frame a on used levels
@@ -413,15 +423,21 @@ int enqueue_pyramids(dis_handle* h) {
                  (l == first ? 2.0 * h->w_org * h->h_org : 0.0) + 8.0 * np_ + (l >= q.lv_l ? 8.0 * np_ : 0.0));
     if (l == first && first > 0) {
       launch_first_level(h->mailbox, first, h->w_org, h->h_org, h->left, h->top, L.g, h->bm_a, h->bm_b, L.Ia, L.Iax,
-                         L.Iay, L.Ib, L.Ibx, L.Iby, h->stream);
+                         L.Iay, L.Ib, L.Ibx, L.Iby, h->stream, only_b);
       h->launches++;
     } else if (l == 0)
       launch_level0(h->mailbox, h->w_org, h->h_org, h->left, h->top, L.g, L.Ia, L.Iax, L.Iay, L.Ib,
-                    L.Ibx, L.Iby, h->stream);
+                    L.Ibx, L.Iby, h->stream, only_b);
     else
       launch_downsample(h->lv[l - 1].g, L.g, h->lv[l - 1].Ia, h->lv[l - 1].Ib, L.Ia, L.Iax, L.Iay, L.Ib,
-                        L.Ibx, L.Iby, h->stream);
+                        L.Ibx, L.Iby, h->stream, only_b);
     h->launches++;
+  }
+  if (h->chained && h->pyr_ev) {  // the next pair of the stream may read this pair's second-frame pyramid from here on
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(h->stream, &cs);
+    CU(h, cudaEventRecordWithFlags(h->pyr_ev, h->stream,
+                                   cs == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault));
   }
   if (h->taps)
     for (int l = first; l <= q.lv_f; ++l) {
@@ -484,7 +500,13 @@ int enqueue_engine(dis_handle* h, const float2* d_initflow) {
   if (fast && q.maxiter > 32)
     return fail(h, DIS_ERR_UNSUPPORTED, "DIS_OPT_ARITH = 1 (tolerance mode) is limited to maxiter <= 32 (got %d)", q.maxiter);
   for (int sl = q.lv_f; sl >= q.lv_l; --sl) {
-    LevelBufs& L = h->lv[sl];
+    LevelBufs L = h->lv[sl];
+    if (h->reuse_a) {  // first frame = second frame of the previous pair of the stream
+      const LevelBufs& P = h->chain_prev->lv[sl];
+      L.Ia = P.Ib;
+      L.Iax = P.Ibx;
+      L.Iay = P.Iby;
+    }
     float t_search = 0, t_dens = 0, t_var = 0;
     const float2* coarse = nullptr;
     if (sl < q.lv_f)
@@ -590,20 +612,21 @@ int enqueue_run_device_batch(dis_handle* h, int n, const uint8_t* const* d_a, co
   }
   auto set_mailbox_now = [&]() { launch_set_mailboxes(h->mailbox, h->bstride, h->nb, m, pitch, h->stream); };
   const bool graphable = h->use_graph && !h->taps && !h->stage_timing && !h->kprof_on;
-  if (graphable && h->graph_exec && h->graph_w == h->w_org && h->graph_h == h->h_org) {
+  const int gv = h->reuse_a ? 1 : 0;
+  if (graphable && (h->graph_w != h->w_org || h->graph_h != h->h_org)) drop_graph(h);
+  if (graphable && h->graph_exec[gv]) {
     Mailbox* mb0 = h->mailbox;
     size_t bs = h->bstride;
     int nb = h->nb, pt = pitch;
     void* args[] = {&mb0, &bs, &nb, &m, &pt};
-    cudaKernelNodeParams kp = h->mb_params;
+    cudaKernelNodeParams kp = h->mb_params[gv];
     kp.kernelParams = args;
     kp.extra = nullptr;
-    CU(h, cudaGraphExecKernelNodeSetParams(h->graph_exec, h->mb_node, &kp));
-    CU(h, cudaGraphLaunch(h->graph_exec, h->stream));
+    CU(h, cudaGraphExecKernelNodeSetParams(h->graph_exec[gv], h->mb_node[gv], &kp));
+    CU(h, cudaGraphLaunch(h->graph_exec[gv], h->stream));
     return DIS_OK;
   }
   if (graphable) {
-    drop_graph(h);
     h->launches = 1;
     CU(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
     set_mailbox_now();  // captured: the root node
@@ -622,21 +645,21 @@ int enqueue_run_device_batch(dis_handle* h, int n, const uint8_t* const* d_a, co
     cudaGraphNodeType ty = cudaGraphNodeTypeEmpty;
     if ((e = cudaGraphGetRootNodes(g, &root, &n_roots)) != cudaSuccess || n_roots != 1 ||
         (e = cudaGraphNodeGetType(root, &ty)) != cudaSuccess || ty != cudaGraphNodeTypeKernel ||
-        (e = cudaGraphKernelNodeGetParams(root, &h->mb_params)) != cudaSuccess) {
+        (e = cudaGraphKernelNodeGetParams(root, &h->mb_params[gv])) != cudaSuccess) {
       cudaGraphDestroy(g);
       return fail(h, DIS_ERR_CUDA, "graph capture: mailbox root node not found (%s)", cudaGetErrorString(e));
     }
-    h->mb_node = root;
-    e = cudaGraphInstantiate(&h->graph_exec, g, 0);
+    h->mb_node[gv] = root;
+    e = cudaGraphInstantiate(&h->graph_exec[gv], g, 0);
     if (e != cudaSuccess) {
       cudaGraphDestroy(g);
       return fail(h, DIS_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
     }
-    h->graph = g;  // kept: mb_node is a node of this graph
+    h->graph[gv] = g;  // kept: mb_node is a node of this graph
     h->graph_w = h->w_org;
     h->graph_h = h->h_org;
     h->tm.launches = h->launches;
-    CU(h, cudaGraphLaunch(h->graph_exec, h->stream));  // the captured arguments are this run's
+    CU(h, cudaGraphLaunch(h->graph_exec[gv], h->stream));  // the captured arguments are this run's
     return DIS_OK;
   }
   set_mailbox_now();
@@ -662,6 +685,27 @@ void reset_timings(dis_handle* h) {
 }
 
 }  // namespace
+
+// ---- pyramid reuse between the consecutive pairs of a stream (used by stream.cu) -------------------------------
+namespace dis {
+int engine_chain(dis_handle* h, dis_handle* prev) {
+  if (!h || !prev || h == prev || h->nb != 1 || prev->nb != 1 || h->device != prev->device) return DIS_ERR_INVALID_ARG;
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaStreamSynchronize(h->stream));
+  if (!h->pyr_ev) CU(h, cudaEventCreateWithFlags(&h->pyr_ev, cudaEventDisableTiming));
+  h->chain_prev = prev;
+  if (!h->chained) {  // second-frame gradients join the workspace: re-plan
+    h->chained = true;
+    const int w = h->w_org, hh = h->h_org;
+    h->lv.clear();
+    h->w_org = h->h_org = 0;
+    return plan(h, w, hh);
+  }
+  return DIS_OK;
+}
+void engine_set_reuse(dis_handle* h, bool reuse) { h->reuse_a = reuse && h->chain_prev != nullptr; }
+cudaEvent_t engine_pyramid_event(dis_handle* h) { return h->pyr_ev; }
+}  // namespace dis
 
 // ================================================================================ C-ABI
 extern "C" {
@@ -839,6 +883,7 @@ int dis_destroy(dis_handle* h) {
   drop_graph(h);
   for (cudaEvent_t e : h->ev)
     if (e) cudaEventDestroy(e);
+  if (h->pyr_ev) cudaEventDestroy(h->pyr_ev);
   if (h->slab) cudaFree(h->slab);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;

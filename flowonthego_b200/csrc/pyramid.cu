@@ -67,13 +67,14 @@ struct SrcPlain {  // unpadded level image (output of k_block_mean)
 template <int NC>
 __global__ void __launch_bounds__(256) k_block_mean(const Mailbox* __restrict__ mb0, int L, int w_org, int h_org,
                                                     int left, int top, int w, int h, float* __restrict__ out_a,
-                                                    float* __restrict__ out_b, size_t bstride) {
+                                                    float* __restrict__ out_b, size_t bstride, int only_b) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= w || y >= h) return;
-  const size_t boff = (size_t)(blockIdx.z >> 1) * bstride;  // grid.z = 2 * pair + frame
+  // grid.z = 2 * pair + frame; only_b (frame a's pyramid is reused from the previous pair of a stream): grid.z = pair
+  const size_t boff = (size_t)(only_b ? blockIdx.z : blockIdx.z >> 1) * bstride;
   const Mailbox* __restrict__ mb = bshift(mb0, boff);
-  const bool second = blockIdx.z & 1;
+  const bool second = only_b || (blockIdx.z & 1);
   const uint8_t* __restrict__ src = second ? mb->b : mb->a;
   float* __restrict__ out = bshift(second ? out_b : out_a, boff);
   const int pitch = mb->pitch, B = 1 << L;
@@ -106,12 +107,12 @@ __global__ void __launch_bounds__(256) k_block_mean(const Mailbox* __restrict__ 
 template <int NC, typename Src>
 __global__ void __launch_bounds__(256) k_pyr_level(Src sa, Src sb, int w, int h, int pad, int pitch,
                                                    int tw, int th, float* Ia, float* Iax, float* Iay,
-                                                   float* Ib, float* Ibx, float* Iby, size_t bstride) {
+                                                   float* Ib, float* Ibx, float* Iby, size_t bstride, int only_b) {
   const int F0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;  // first float column of this thread
   const int Y = blockIdx.y * blockDim.y + threadIdx.y;
   if (F0 >= pitch || Y >= th) return;
-  const bool second = blockIdx.z & 1;  // grid.z = 2 * pair + frame
-  const size_t boff = (size_t)(blockIdx.z >> 1) * bstride;
+  const bool second = only_b || (blockIdx.z & 1);  // grid.z = 2 * pair + frame (only_b: grid.z = pair)
+  const size_t boff = (size_t)(only_b ? blockIdx.z : blockIdx.z >> 1) * bstride;
   Src s = second ? sb : sa;
   s.shift(boff);
   s.resolve();
@@ -149,11 +150,11 @@ __global__ void __launch_bounds__(256) k_pyr_level(Src sa, Src sb, int w, int h,
 
 template <int NC, typename Src>
 void launch(Src sa, Src sb, const LevelGeom& g, float* Ia, float* Iax, float* Iay, float* Ib,
-            float* Ibx, float* Iby, cudaStream_t st) {
+            float* Ibx, float* Iby, cudaStream_t st, int only_b) {
   dim3 block(64, 4);
-  dim3 grid((g.pitch / 4 + block.x - 1) / block.x, (g.th + block.y - 1) / block.y, 2 * g.nb);
+  dim3 grid((g.pitch / 4 + block.x - 1) / block.x, (g.th + block.y - 1) / block.y, (only_b ? 1 : 2) * g.nb);
   k_pyr_level<NC, Src><<<grid, block, 0, st>>>(sa, sb, g.w, g.h, g.pad, g.pitch, g.tw, g.th, Ia, Iax, Iay,
-                                               Ib, Ibx, Iby, g.bstride);
+                                               Ib, Ibx, Iby, g.bstride, only_b);
 }
 
 }  // namespace
@@ -174,13 +175,13 @@ void launch_set_mailboxes(Mailbox* mb0, size_t bstride, int nb, const MailboxBat
 }
 
 void launch_level0(const Mailbox* mb, int w_org, int h_org, int left, int top, const LevelGeom& g, float* Ia,
-                   float* Iax, float* Iay, float* Ib, float* Ibx, float* Iby, cudaStream_t st) {
+                   float* Iax, float* Iay, float* Ib, float* Ibx, float* Iby, cudaStream_t st, int only_b) {
   if (g.noc == 3) {
     SrcU8<3> sa{mb, 0, nullptr, w_org, h_org, 0, left, top}, sb{mb, 1, nullptr, w_org, h_org, 0, left, top};
-    launch<3>(sa, sb, g, Ia, Iax, Iay, Ib, Ibx, Iby, st);
+    launch<3>(sa, sb, g, Ia, Iax, Iay, Ib, Ibx, Iby, st, only_b);
   } else {
     SrcU8<1> sa{mb, 0, nullptr, w_org, h_org, 0, left, top}, sb{mb, 1, nullptr, w_org, h_org, 0, left, top};
-    launch<1>(sa, sb, g, Ia, Iax, Iay, Ib, Ibx, Iby, st);
+    launch<1>(sa, sb, g, Ia, Iax, Iay, Ib, Ibx, Iby, st, only_b);
   }
 }
 
@@ -188,28 +189,28 @@ void launch_level0(const Mailbox* mb, int w_org, int h_org, int left, int top, c
 // bm_a / bm_b (g.w x g.h x noc floats), then the padded image + gradients from those.
 void launch_first_level(const Mailbox* mb, int L, int w_org, int h_org, int left, int top, const LevelGeom& g,
                         float* bm_a, float* bm_b, float* Ia, float* Iax, float* Iay, float* Ib, float* Ibx, float* Iby,
-                        cudaStream_t st) {
-  dim3 block(32, 8), grid((g.w + 31) / 32, (g.h + 7) / 8, 2 * g.nb);
+                        cudaStream_t st, int only_b) {
+  dim3 block(32, 8), grid((g.w + 31) / 32, (g.h + 7) / 8, (only_b ? 1 : 2) * g.nb);
   if (g.noc == 3) {
-    k_block_mean<3><<<grid, block, 0, st>>>(mb, L, w_org, h_org, left, top, g.w, g.h, bm_a, bm_b, g.bstride);
+    k_block_mean<3><<<grid, block, 0, st>>>(mb, L, w_org, h_org, left, top, g.w, g.h, bm_a, bm_b, g.bstride, only_b);
     SrcPlain<3> sa{bm_a, g.w}, sb{bm_b, g.w};
-    launch<3>(sa, sb, g, Ia, Iax, Iay, Ib, Ibx, Iby, st);
+    launch<3>(sa, sb, g, Ia, Iax, Iay, Ib, Ibx, Iby, st, only_b);
   } else {
-    k_block_mean<1><<<grid, block, 0, st>>>(mb, L, w_org, h_org, left, top, g.w, g.h, bm_a, bm_b, g.bstride);
+    k_block_mean<1><<<grid, block, 0, st>>>(mb, L, w_org, h_org, left, top, g.w, g.h, bm_a, bm_b, g.bstride, only_b);
     SrcPlain<1> sa{bm_a, g.w}, sb{bm_b, g.w};
-    launch<1>(sa, sb, g, Ia, Iax, Iay, Ib, Ibx, Iby, st);
+    launch<1>(sa, sb, g, Ia, Iax, Iay, Ib, Ibx, Iby, st, only_b);
   }
 }
 
 void launch_downsample(const LevelGeom& gf, const LevelGeom& gc, const float* Ia_f, const float* Ib_f,
                        float* Ia, float* Iax, float* Iay, float* Ib, float* Ibx, float* Iby,
-                       cudaStream_t st) {
+                       cudaStream_t st, int only_b) {
   if (gc.noc == 3) {
     SrcDown<3> sa{Ia_f, gf.pitch, gf.pad}, sb{Ib_f, gf.pitch, gf.pad};
-    launch<3>(sa, sb, gc, Ia, Iax, Iay, Ib, Ibx, Iby, st);
+    launch<3>(sa, sb, gc, Ia, Iax, Iay, Ib, Ibx, Iby, st, only_b);
   } else {
     SrcDown<1> sa{Ia_f, gf.pitch, gf.pad}, sb{Ib_f, gf.pitch, gf.pad};
-    launch<1>(sa, sb, gc, Ia, Iax, Iay, Ib, Ibx, Iby, st);
+    launch<1>(sa, sb, gc, Ia, Iax, Iay, Ib, Ibx, Iby, st, only_b);
   }
 }
 

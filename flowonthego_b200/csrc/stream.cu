@@ -9,6 +9,12 @@
 // frame slots.  Frame k is uploaded ONCE, on the stream of the pair that consumes it as its second image
 // (pair k-1); pair k, on the next handle, waits for that upload through an event.  So a pair costs one u8
 // frame of H2D traffic instead of two, and up to `depth` pairs overlap their copies and kernels.
+//
+// Pyramid reuse ("frame k+1's pyramid is reused as the next pair's first image"): with depth >= 2
+// the handles are chained (engine_chain): pair k builds only the pyramid of its second frame (with gradients) and
+// reads its first frame's pyramid from the workspace of the handle that ran pair k-1, once that handle's pyramid
+// event has fired.  A handle may overwrite its second-frame pyramid only after the pair that reads it as first frame
+// has finished (the `done` event of the next handle).  The arithmetic per frame is unchanged, so is every flow.
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -31,6 +37,8 @@ struct dis_video {
   std::vector<float*> host_out;        // per handle: destination of the pair in flight
   long long pushed = 0;                // frames pushed so far
   long long popped = 0;                // pairs handed back so far
+  bool chained = false;                // engine_chain done (workspaces hold the second frame's gradients)
+  bool reuse = false;                  // pyramids shared between consecutive pairs
 };
 
 namespace {
@@ -73,6 +81,13 @@ int dis_video_create(const dis_params* params, int channels, int w, int h, int d
     v->eng.push_back(e);
   }
   dis_level_flow_size(v->eng[0], &v->lw, &v->lh);
+  // Pyramid reuse is on by default for shallow pipelines (live streams, where it shortens a pair's critical path) and
+  // off for deep ones: measured on the C5 stream at depth 64, the dependency between consecutive pairs costs more
+  // (6 980 pairs/s) than the saved pyramid work brings (7 180 without).  dis_video_set_reuse() overrides.
+  if (depth >= 2 && depth <= 8) {
+    const int rc = dis_video_set_reuse(v, 1);
+    if (rc != DIS_OK) return bail(rc);
+  }
   if (cudaSetDevice(device) != cudaSuccess) return bail(DIS_ERR_CUDA);
   for (int i = 0; i < depth + 2; ++i) {
     uint8_t* p = nullptr;
@@ -109,6 +124,31 @@ void dis_video_destroy(dis_video* v) {
   for (cudaEvent_t e : v->done) cudaEventDestroy(e);
   delete v;
 }
+
+int dis_video_set_reuse(dis_video* v, int on) {
+  if (!v || dis_video_pending(v) > 0 || v->pushed > 0) {
+    dis::set_global_error("dis_video_set_reuse: only before the first frame is pushed");
+    return DIS_ERR_INVALID_ARG;
+  }
+  if (on && v->depth < 2) {
+    dis::set_global_error("dis_video_set_reuse: needs depth >= 2");
+    return DIS_ERR_INVALID_ARG;
+  }
+  if (on && !v->chained) {  // pair k reads its first frame's pyramid from the handle of pair k-1
+    for (int i = 0; i < v->depth; ++i) {
+      const int rc = dis::engine_chain(v->eng[i], v->eng[(i + v->depth - 1) % v->depth]);
+      if (rc != DIS_OK) {
+        dis::set_global_error("%s", dis_last_error(v->eng[i]));
+        return rc;
+      }
+    }
+    v->chained = true;
+  }
+  v->reuse = on != 0;
+  return DIS_OK;
+}
+
+int dis_video_reuse(const dis_video* v) { return v && v->reuse ? 1 : 0; }
 
 int dis_video_set_output(dis_video* v, int mode) {
   if (!v || (mode != DIS_VIDEO_OUT_LEVEL && mode != DIS_VIDEO_OUT_FULL) || dis_video_pending(v) > 0) {
@@ -179,7 +219,18 @@ int dis_video_push(dis_video* v, const uint8_t* frame, int pitch, float* flow_ou
   ++v->pushed;
   if (f == 0) return DIS_OK;
   const int prev = (int)((f - 1) % nslots);
-  CUV(cudaStreamWaitEvent(st, v->uploaded[prev], 0));  // first image was uploaded on the previous pair's stream
+  const long long pair = f - 1;
+  const bool reuse = v->reuse && pair >= 1;  // pair - 1 built this pair's first frame as its second one
+  if (reuse) {
+    // its pyramid (and with it the upload) is ready when the previous handle's pyramid event fires ...
+    CUV(cudaStreamWaitEvent(st, dis::engine_pyramid_event(v->eng[(k + v->depth - 1) % v->depth]), 0));
+    // ... and this handle's own second-frame pyramid, about to be overwritten, was the first frame of the pair that
+    // ran on the next handle depth-1 pairs ago
+    if (pair >= v->depth) CUV(cudaStreamWaitEvent(st, v->done[(k + 1) % v->depth], 0));
+  } else {
+    CUV(cudaStreamWaitEvent(st, v->uploaded[prev], 0));  // first image was uploaded on the previous pair's stream
+  }
+  dis::engine_set_reuse(v->eng[k], reuse);
   const int rc = dis_submit_u8_device(v->eng[k], v->d_frame[prev], v->d_frame[slot], v->w, v->h, (int)rowb, v->d_flow[k]);
   if (rc != DIS_OK) {
     dis::set_global_error("%s", dis_last_error(v->eng[k]));
@@ -191,6 +242,7 @@ int dis_video_push(dis_video* v, const uint8_t* frame, int pitch, float* flow_ou
   } else {
     CUV(cudaMemcpyAsync(flow_out, v->d_flow[k], v->flow_floats * sizeof(float), cudaMemcpyDeviceToHost, st));
   }
+  CUV(cudaEventRecord(v->done[k], st));
   v->host_out[k] = flow_out;
   return DIS_OK;
 }

@@ -229,6 +229,12 @@ void dis_video_destroy(dis_video* v);
  * 1080p pair).  The computation is the same either way.  Only while no pair is in flight. */
 typedef enum dis_video_output { DIS_VIDEO_OUT_LEVEL = 0, DIS_VIDEO_OUT_FULL = 1 } dis_video_output;
 int dis_video_set_output(dis_video* v, int mode);
+/* Pyramid reuse between consecutive pairs: pair k builds only its second frame's pyramid and takes the
+ * first frame's from pair k-1.  Same results bit for bit; shortens a pair's critical path but makes pair k wait for
+ * pair k-1's pyramid, which costs throughput in deep pipelines.  Default: on for 2 <= depth <= 8, off otherwise.
+ * Only before the first frame is pushed; needs depth >= 2. */
+int dis_video_set_reuse(dis_video* v, int on);
+int dis_video_reuse(const dis_video* v);
 /* Floats per flow field handed back in the current output mode, and its width / height. */
 size_t dis_video_flow_size(const dis_video* v, int* w_out, int* h_out);
 /* k-th engine handle (0 <= k < depth) -- e.g. for dis_stream(); owned by the video object. */

@@ -28,12 +28,15 @@ def bits_differ(x, y):
                 np.ascontiguousarray(y, np.float32).view(np.uint32)).sum())
 
 
-@pytest.mark.parametrize("channels,depth", [(1, 3), (1, 1), (3, 2)])
-def test_stream_equals_pairwise(channels, depth):
-    w, h, n = 322, 198, 8
+@pytest.mark.parametrize("channels,depth,reuse", [(1, 3, None), (1, 1, None), (3, 2, None), (1, 3, False), (1, 12, True)])
+def test_stream_equals_pairwise(channels, depth, reuse):
+    """Every flow of the pipelined sequence equals a separate run on that pair -- with and without pyramid reuse
+    between consecutive pairs (default: on for 2 <= depth <= 8)."""
+    w, h, n = 322, 198, 8 if depth < 12 else 30
     frames = sequence(w, h, n, channels=channels)
     p = F.Params.preset(2, 1024, verbosity=0).copy(lv_f=3, lv_l=1)
-    with F.FlowStream(p, w, h, depth=depth, channels=channels, output="full") as s:
+    with F.FlowStream(p, w, h, depth=depth, channels=channels, output="full", reuse=reuse) as s:
+        assert s.reuse == ((2 <= depth <= 8) if reuse is None else reuse)
         flows = list(s.flows(frames))
         assert s.pending == 0
     with F.FlowStream(p, w, h, depth=depth, channels=channels) as s:  # default: the engine's level-lv_l output
@@ -44,8 +47,10 @@ def test_stream_equals_pairwise(channels, depth):
         for k in range(n - 1):
             assert bits_differ(flows[k], e.run_u8(frames[k], frames[k + 1])) == 0, k
             assert bits_differ(lflows[k], e.level_flow(w, h)) == 0, k
-    # and the oracle on one pair, so that this file stands on its own
+    # and the oracle on one pair, so that this file stands on its own (pair 2 has a reused first-frame pyramid)
     assert bits_differ(flows[2], port.run_u8(frames[2], frames[3], p.to_dict())) == 0
+    with pytest.raises(F.DisError):
+        F.FlowStream(p, w, h, depth=1, reuse=True)
 
 
 def test_stream_protocol_errors():
