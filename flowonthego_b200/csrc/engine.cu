@@ -19,6 +19,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/dis_c.h"
 #include "common.cuh"
 #include "imgio.h"
@@ -37,6 +39,19 @@ thread_local std::string g_create_error;
 struct ConnectionsDefault {
   ConnectionsDefault() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
 } g_connections_default;
+
+// NVTX ranges around the stages (tracing).  Host-side: they bracket the enqueue of a stage, i.e.
+// the kernels themselves when a run is launched kernel by kernel (DIS_OPT_USE_GRAPH = 0, taps, profiling) and the
+// capture when it is recorded into a graph; a replayed graph shows up as one "dis:run" range.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  NvtxRange(const char* fmt, int v) {
+    char buf[48];
+    snprintf(buf, sizeof buf, fmt, v);
+    nvtxRangePushA(buf);
+  }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 struct LevelBufs {
   LevelGeom g{};
@@ -407,6 +422,7 @@ void tap_image(dis_handle* h, int tap, int level, const float* d, const LevelGeo
 
 // stage 1 (kroeger/run_dense.cpp:298-344): pyramids of both frames from the u8 inputs
 int enqueue_pyramids(dis_handle* h) {
+  NvtxRange nv("dis:pyramids");
   const dis_params& q = h->P;
   // Product path: nothing reads the levels below lv_l (the engine starts at lv_l, oflow.cpp:199), so the first
   // processed level is built straight from the u8 frames (bit-identical, see k_block_mean) and the finer levels are
@@ -514,6 +530,7 @@ int enqueue_engine(dis_handle* h, const float2* d_initflow) {
     else if (d_initflow)
       coarse = d_initflow;
     {
+      NvtxRange nv("dis:search L%d", sl);
       StageClock ck(h, &h->tm.search_ms);
       PatchSearchArgs pa{L.Ia, L.Iax, L.Iay, L.Ib, L.g, h->opt, coarse, h->pflow, h->pweight};
       // SURVEY 8(d) B_D: 4 padded arrays in, coarse flow in, patch results out
@@ -538,6 +555,7 @@ int enqueue_engine(dis_handle* h, const float2* d_initflow) {
     }
     tap_store(h, DIS_TAP_PATCH_FLOW, sl, h->pflow, (size_t)L.g.nop * 2);
     {
+      NvtxRange nv("dis:densify L%d", sl);
       StageClock ck(h, &h->tm.densify_ms);
       DensifyArgs da{L.g, h->opt, h->pflow, h->pweight, fb ? h->pflow_bw : nullptr, fb ? h->pweight_bw : nullptr,
                      L.flow, h->fb_anchor, h->fb_wbil, h->fb_maxdisp, (h->opt.p + h->opt.steps - 1) / h->opt.steps};
@@ -555,6 +573,7 @@ int enqueue_engine(dis_handle* h, const float2* d_initflow) {
     }
     tap_store(h, DIS_TAP_FLOW_DENSE, sl, L.flow, (size_t)L.g.w * L.g.h * 2);
     if (q.usetvref) {
+      NvtxRange nv("dis:refine L%d", sl);
       StageClock ck(h, &h->tm.varref_ms);
       vp.n_inner = q.tv_innerit * (sl + 1);  // refine_variational.cpp:36
       int n = (fast ? launch_varref_fast : launch_varref)(L.g, vp, L.Ia, L.Ib, L.flow, h->vb, h->stream, prof);
@@ -578,6 +597,7 @@ int enqueue_engine(dis_handle* h, const float2* d_initflow) {
 }
 
 int enqueue_finish(dis_handle* h) {
+  NvtxRange nv("dis:finish");
   const LevelBufs& L = h->lv[h->P.lv_l];
   ProfScope ps(h->kprof_on ? &h->kprof : nullptr, "k_finish", h->P.lv_l,
                8.0 * (double)L.g.w * L.g.h + 8.0 * (double)h->w_org * h->h_org);
@@ -599,6 +619,7 @@ int enqueue_run_device(dis_handle* h, const uint8_t* d_a, const uint8_t* d_b, in
 // n <= nb pairs; the unused slots of a batched handle recompute pair 0 into their own scratch output
 int enqueue_run_device_batch(dis_handle* h, int n, const uint8_t* const* d_a, const uint8_t* const* d_b, int pitch,
                              float2* const* d_out) {
+  NvtxRange nv("dis:run");
   // Per-run pointers go to the device mailbox through a one-block kernel.  On the graph path that kernel is the
   // graph's ROOT node and its arguments are patched before every launch (cudaGraphExecKernelNodeSetParams): a
   // separate launch in front of (or behind) each graph launch costs ~70 us of throughput per pair-run when many

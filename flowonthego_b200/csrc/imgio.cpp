@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 
 namespace {
 
@@ -28,6 +29,11 @@ inline uint8_t gray_cv(int r, int g, int b) { return (uint8_t)((b * 1868 + g * 9
 // cv2.imread(IMREAD_GRAYSCALE) (OpenCV 4.13) on the reference's RGB frames images/alley_1/*.png.
 inline uint8_t gray_png(int r, int g, int b) { return (uint8_t)((9797 * r + 19234 * g + 3737 * b) >> 15); }
 
+// Largest accepted image edge (the .flo reader uses the same bound): keeps every size computation below far from
+// overflow and a malformed header from requesting gigabytes.
+constexpr long kMaxDim = 99999;
+constexpr size_t kMaxPixels = (size_t)1 << 30;
+
 std::string read_pnm(const std::vector<uint8_t>& d, int want, GrayImage* out) {
   size_t p = 2;
   auto next_int = [&](int* v) {
@@ -42,7 +48,10 @@ std::string read_pnm(const std::vector<uint8_t>& d, int want, GrayImage* out) {
     }
     if (p >= d.size() || d[p] < '0' || d[p] > '9') return false;
     long x = 0;
-    while (p < d.size() && d[p] >= '0' && d[p] <= '9') x = x * 10 + (d[p++] - '0');
+    while (p < d.size() && d[p] >= '0' && d[p] <= '9') {
+      x = x * 10 + (d[p++] - '0');
+      if (x > kMaxDim) return false;  // no header integer of a valid file is larger (also stops overflow)
+    }
     *v = (int)x;
     return true;
   };
@@ -51,8 +60,9 @@ std::string read_pnm(const std::vector<uint8_t>& d, int want, GrayImage* out) {
   if (!next_int(&w) || !next_int(&h) || !next_int(&mx)) return "bad PNM header";
   if (mx != 255) return "only 8-bit PNM supported";
   ++p;  // single whitespace after maxval
+  if (w <= 0 || h <= 0 || (size_t)w * h > kMaxPixels) return "bad PNM size";
   const size_t need = (size_t)w * h * (color ? 3 : 1);
-  if (w <= 0 || h <= 0 || p + need > d.size()) return "truncated PNM";
+  if (p + need > d.size()) return "truncated PNM";
   out->w = w;
   out->h = h;
   out->ch = want;
@@ -85,6 +95,8 @@ std::string read_png(const std::vector<uint8_t>& d, int want, GrayImage* out) {
     if (p + 12 + len > d.size()) return "truncated PNG";
     const uint8_t* body = &d[p + 8];
     if (!memcmp(type, "IHDR", 4)) {
+      if (len != 13) return "bad PNG header";
+      if (be32(body) > (uint32_t)kMaxDim || be32(body + 4) > (uint32_t)kMaxDim) return "PNG too large";
       w = (int)be32(body);
       h = (int)be32(body + 4);
       depth = body[8];
@@ -99,7 +111,7 @@ std::string read_png(const std::vector<uint8_t>& d, int want, GrayImage* out) {
     }
     p += 12 + len;
   }
-  if (w <= 0 || h <= 0) return "bad PNG header";
+  if (w <= 0 || h <= 0 || (size_t)w * h > kMaxPixels) return "bad PNG header";
   if (depth != 8 || interlace != 0) return "only 8-bit non-interlaced PNG supported";
   int ch;
   switch (ctype) {
@@ -223,9 +235,13 @@ std::string read_gray_image(const char* path, GrayImage* out) { return read_imag
 
 std::string read_image(const char* path, int channels, GrayImage* out) {
   if (channels != 1 && channels != 3) return "channels must be 1 or 3";
-  std::vector<uint8_t> d;
-  if (!read_file(path, &d)) return std::string("cannot read ") + path;
-  if (d.size() > 2 && d[0] == 'P' && (d[1] == '5' || d[1] == '6')) return read_pnm(d, channels, out);
-  if (d.size() > 8 && d[0] == 0x89 && d[1] == 'P') return read_png(d, channels, out);
-  return "unsupported image format (PNG, PGM and PPM are read natively; convert others first)";
+  try {  // nothing may propagate through the extern "C" callers (std::bad_alloc on a hostile header)
+    std::vector<uint8_t> d;
+    if (!read_file(path, &d)) return std::string("cannot read ") + path;
+    if (d.size() > 2 && d[0] == 'P' && (d[1] == '5' || d[1] == '6')) return read_pnm(d, channels, out);
+    if (d.size() > 8 && d[0] == 0x89 && d[1] == 'P') return read_png(d, channels, out);
+    return "unsupported image format (PNG, PGM and PPM are read natively; convert others first)";
+  } catch (const std::exception& e) {
+    return std::string("image decode failed: ") + e.what();
+  }
 }

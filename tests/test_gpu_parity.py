@@ -487,3 +487,48 @@ def test_randomized_configurations():
         assert bits_differ(got, ref) == 0, (case, ch, w, h, kw)
         ran += 1
     assert ran >= 20
+
+
+def test_pageable_buffers_and_row_pitch():
+    """dis_submit_u8 / dis_run_u8 with ordinary (non-pinned) host memory and a row pitch larger than the width."""
+    w, h, pitch = 333, 201, 352
+    a, b, _ = synth_pair(w, h, seed=21)
+    big_a, big_b = np.full((h, pitch), 77, np.uint8), np.full((h, pitch), 99, np.uint8)
+    big_a[:, :w], big_b[:, :w] = a, b
+    va, vb = big_a[:, :w], big_b[:, :w]          # views: strides (352, 1)
+    assert va.strides == (pitch, 1) and not va.flags["C_CONTIGUOUS"]
+    p = params(2, 1024, lv_f=3, lv_l=1)
+    ref = port.run_u8(a, b, p.to_dict())
+    out = np.empty((h, w, 2), np.float32)        # pageable result buffer
+    with F.Engine(p, w, h) as e:
+        assert bits_differ(e.run_u8(va, vb, out), ref) == 0
+        e.submit_u8(va, vb, out)                 # asynchronous form, same buffers
+        assert bits_differ(e.wait(), ref) == 0
+        with pytest.raises(F.DisError):          # pitch smaller than a row
+            api._check(F.lib().dis_run_u8(e._h, va.ctypes.data, vb.ctypes.data, w, h, w - 1, api._as_fp(out)), e._h)
+
+
+def test_two_processes_share_one_gpu(tmp_path):
+    """Two host processes, each with its own handle and context on the same device, run concurrently."""
+    import subprocess
+    import sys
+    script = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "import flowonthego_b200 as F\n"
+        "from oracle import port\n"
+        "from tests.synth import synth_pair\n"
+        "seed = int(sys.argv[1])\n"
+        "a, b, _ = synth_pair(320, 200, seed=seed)\n"
+        "p = F.Params.preset(2, 1024, verbosity=0).copy(lv_f=3, lv_l=1)\n"
+        "ref = port.run_u8(a, b, p.to_dict())\n"
+        "with F.Engine(p, 320, 200) as e:\n"
+        "    for _ in range(20):\n"
+        "        got = e.run_u8(a, b)\n"
+        "        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))\n"
+        "print('ok', seed)\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    procs = [subprocess.Popen([sys.executable, "-c", script, str(s)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for s in (31, 32)]
+    for s, pr in zip((31, 32), procs):
+        out, err = pr.communicate(timeout=300)
+        assert pr.returncode == 0 and out.strip() == "ok %d" % s, err[-2000:]

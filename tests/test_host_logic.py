@@ -132,3 +132,27 @@ def test_cli_binaries_usage_and_loud_failure(tmp_path, golden_dir):
     b = os.path.join(golden_dir, "alley_0002_gray.png")
     r = subprocess.run([os.path.join(bindir, "run_dense"), a, b, str(tmp_path / "o.flo")], capture_output=True, text=True)
     assert r.returncode == 1 and "run_dense:" in r.stderr and not (tmp_path / "o.flo").exists()
+
+
+def test_image_reader_rejects_malformed_files(tmp_path):
+    """Hostile headers must come back as DIS_ERR_IO, not as an abort or a multi-gigabyte allocation."""
+    import struct
+    import zlib
+    import flowonthego_b200 as F
+
+    def chunk(t, body):
+        return struct.pack(">I", len(body)) + t + body + struct.pack(">I", zlib.crc32(t + body))
+    sig = b"\x89PNG\r\n\x1a\n"
+    cases = {
+        "short_ihdr.png": sig + chunk(b"IHDR", b"\0\0\0\x10\0\0\0\x10\x08") + chunk(b"IEND", b""),
+        "huge.png": sig + chunk(b"IHDR", struct.pack(">IIBBBBB", 0x7fffffff, 0x7fffffff, 8, 0, 0, 0, 0)) + chunk(b"IEND", b""),
+        "big_area.png": sig + chunk(b"IHDR", struct.pack(">IIBBBBB", 90000, 90000, 8, 0, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(b"\0" * 64)) + chunk(b"IEND", b""),
+        "huge.pgm": b"P5\n99999999999999999999 5\n255\n" + b"\0" * 16,
+        "trunc.pgm": b"P5\n64 64\n255\n" + b"\0" * 100,
+    }
+    for name, data in cases.items():
+        path = tmp_path / name
+        path.write_bytes(data)
+        with pytest.raises(F.DisError) as ei:
+            F.read_image_gray(str(path))
+        assert ei.value.code == 4, name  # DIS_ERR_IO

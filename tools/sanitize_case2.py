@@ -1,4 +1,4 @@
-"""compute-sanitizer targets added later in round 1: colour engine, batched handle, group, video front end,
+"""compute-sanitizer targets added later in round 1: colour engine, batched handle, level export, tolerance mode, video front end (with pyramid reuse),
 colour coding / EPE, level-2 upsampling kernel.  Small sizes; every result is checked against the oracle."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -23,15 +23,22 @@ with F.Engine(p, w, h, batch=nb) as e:
     e.submit_u8_device_batch([x.data_ptr() for x in da], [x.data_ptr() for x in db], w, h, w, [out[k].data_ptr() for k in range(nb)])
     e.wait()
     print("batched:", [bd(out[k].cpu().numpy(), port.run_u8(pairs[k][0], pairs[k][1], p.to_dict())) for k in range(nb)], flush=True)
-# group of 2
-with F.EngineGroup(p, w, h, 2) as g:
-    out.zero_()
-    g.submit_u8_device([da[0].data_ptr(), da[1].data_ptr()], [db[0].data_ptr(), db[1].data_ptr()], w, h, w, [out[0].data_ptr(), out[1].data_ptr()])
-    g.wait()
-    print("group:", [bd(out[k].cpu().numpy(), port.run_u8(pairs[k][0], pairs[k][1], p.to_dict())) for k in range(2)], flush=True)
+# level-flow export folded into the finish kernel + tolerance-mode kernels (DIS_OPT_ARITH)
+with F.Engine(p, w, h, batch=nb) as e:
+    stage = torch.zeros((nb,) + e.level_flow_shape(), dtype=torch.float32, device="cuda")
+    e.set_level_export([stage[k].data_ptr() for k in range(nb)])
+    e.submit_u8_device_batch([x.data_ptr() for x in da], [x.data_ptr() for x in db], w, h, w, [out[k].data_ptr() for k in range(nb)])
+    e.wait()
+    print("level export:", [bd(stage[k].cpu().numpy(), port.run_u8(pairs[k][0], pairs[k][1], p.to_dict(), want_level=True)[1]) for k in range(nb)], flush=True)
+with F.Engine(p, w, h) as e:
+    from flowonthego_b200 import api
+    e.set_option(api.OPT_ARITH, 1)
+    d = np.abs(e.run_u8(*pairs[0]) - port.run_u8(pairs[0][0], pairs[0][1], p.to_dict()))
+    print("fast mode: max |d| %.2g" % d.max(), flush=True)
 # video front end
 frames = [pairs[0][0], pairs[0][1], pairs[1][1], pairs[2][1]]
-with F.FlowStream(p, w, h, depth=2) as s:
+with F.FlowStream(p, w, h, depth=2, output="full") as s:  # depth 2: pyramids reused between consecutive pairs
+    assert s.reuse
     fl = list(s.flows(frames))
 print("video:", [bd(fl[k], port.run_u8(frames[k], frames[k + 1], p.to_dict())) for k in range(3)], flush=True)
 # colour coding + EPE
