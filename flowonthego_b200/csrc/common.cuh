@@ -36,6 +36,12 @@ __host__ __device__ __forceinline__ T* bshift(T* p, size_t off) {
   return p ? reinterpret_cast<T*>(reinterpret_cast<uintptr_t>(p) + off) : nullptr;
 }
 
+// the same for a pointer that is never null (no select: kernels shift a dozen pointers per thread)
+template <class T>
+__host__ __device__ __forceinline__ T* bshift_nn(T* p, size_t off) {
+  return reinterpret_cast<T*>(reinterpret_cast<uintptr_t>(p) + off);
+}
+
 // Parameters derived in OFClass::OFClass (kroeger/oflow.cpp:75-108)
 struct OptParams {
   int p, novals, steps, max_iter, min_iter, patnorm, costfct, noc;
@@ -124,6 +130,10 @@ void launch_densify(const DensifyArgs& a, cudaStream_t st);
 // varref.cu
 struct VarRefBuffers {
   float *avg, *Iz, *mask, *Ix, *Iy, *Ixx, *Ixy, *Iyy, *Ixz, *Iyz;  // planar, w*h
+  // the ten arrays above are one allocation: array k (order avg, Iz, Ix, Iy, Ixx, Ixy, Iyy, Ixz, Iyz, mask) starts at
+  // stack + k * astride floats, so that a kernel needs one shifted base pointer instead of ten (k_assemble)
+  float* stack;
+  unsigned astride;
   float4 *coefA, *coefB;  // wavefront-major {a11,a12,a22,horiz} (inverted 2x2 blocks) and {b1,b2,vert,-}
   float4* du4;            // wavefront-major records {du, dv, tag, -}
   int* progress;          // SOR wavefront flags: counters, ticket, epoch

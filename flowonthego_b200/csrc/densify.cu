@@ -68,14 +68,14 @@ __global__ void __launch_bounds__(256, 2) k_densify(const DensifyArgs a) {
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= a.g.w || y >= a.g.h) return;
   const size_t boff = (size_t)blockIdx.z * a.g.bstride;  // blockIdx.z = pair of a batched handle
-  const float2* __restrict__ q_pflow = bshift(a.pflow, boff);
-  const float* __restrict__ q_pweight = bshift(a.pweight, boff);
+  const float2* __restrict__ q_pflow = bshift_nn(a.pflow, boff);  // never null (the backward-grid pointers may be)
+  const float* __restrict__ q_pweight = bshift_nn(a.pweight, boff);
   const float2* __restrict__ q_pflow_bw = bshift(a.pflow_bw, boff);
   const float* __restrict__ q_pweight_bw = bshift(a.pweight_bw, boff);
   const int2* __restrict__ q_anchor = bshift(a.anchor, boff);
   const float4* __restrict__ q_wbil = bshift(a.wbil, boff);
   const int* __restrict__ q_maxdisp = bshift(a.maxdisp, boff);
-  float2* __restrict__ q_flow = bshift(a.flow, boff);
+  float2* __restrict__ q_flow = bshift_nn(a.flow, boff);
   const int P = a.o.p, N = a.o.novals, steps = a.o.steps, half = P / 2;
   // patches whose footprint [c-half, c+half-1] contains the pixel
   // c = g*steps + off  =>  g in [ceil((x-off-half+1)/steps), floor((x-off+half)/steps)]

@@ -306,9 +306,10 @@ size_t carve(dis_handle* h, int w, int h_img, char* base, bool assign) {
   VarRefBuffers vb{};
   if (q.usetvref) {
     const size_t n = (size_t)gf.w * gf.h;
-    float** planes[] = {&vb.avg, &vb.Iz, &vb.Ix, &vb.Iy, &vb.Ixx, &vb.Ixy, &vb.Iyy, &vb.Ixz, &vb.Iyz};
-    for (float** p : planes) *p = c.take<float>(n * h->noc);  // one plane per colour channel
-    vb.mask = c.take<float>(n);
+    float** planes[] = {&vb.avg, &vb.Iz, &vb.Ix, &vb.Iy, &vb.Ixx, &vb.Ixy, &vb.Iyy, &vb.Ixz, &vb.Iyz, &vb.mask};
+    vb.astride = (unsigned)align_up(n * h->noc, 64);  // one plane per colour channel (the mask has one)
+    vb.stack = c.take<float>((size_t)vb.astride * 10);
+    for (int k = 0; k < 10; ++k) *planes[k] = vb.stack ? vb.stack + (size_t)k * vb.astride : nullptr;
     size_t n_coef4, n_du4, n_prog;
     varref_sizes(gf.w, gf.h, std::max(1, q.tv_solverit), &n_coef4, &n_du4, &n_prog);
     vb.coefA = c.take<float4>(n_coef4);

@@ -25,8 +25,8 @@ __device__ __forceinline__ void export_level(const float2* __restrict__ fl, int 
 __global__ void __launch_bounds__(256) k_finish(const float2* __restrict__ fl, int wl, int hl, int lv_l,
                                                 int left, int top, int w_org, int h_org,
                                                 const Mailbox* __restrict__ mb, size_t bstride) {
-  fl = bshift(fl, (size_t)blockIdx.z * bstride);  // blockIdx.z = pair of a batched handle
-  mb = bshift(mb, (size_t)blockIdx.z * bstride);
+  fl = bshift_nn(fl, (size_t)blockIdx.z * bstride);  // blockIdx.z = pair of a batched handle
+  mb = bshift_nn(mb, (size_t)blockIdx.z * bstride);
   float2* __restrict__ out = mb->out;
   export_level(fl, wl * hl, mb);
   const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -85,8 +85,8 @@ __global__ void __launch_bounds__(256) k_finish(const float2* __restrict__ fl, i
 // touch the border clamps or the crop edge fall back to the per-pixel form.
 __global__ void __launch_bounds__(256) k_finish_x4(const float2* __restrict__ fl, int wl, int hl, int left, int top,
                                                    int w_org, int h_org, const Mailbox* __restrict__ mb, size_t bstride) {
-  fl = bshift(fl, (size_t)blockIdx.z * bstride);  // blockIdx.z = pair of a batched handle
-  mb = bshift(mb, (size_t)blockIdx.z * bstride);
+  fl = bshift_nn(fl, (size_t)blockIdx.z * bstride);  // blockIdx.z = pair of a batched handle
+  mb = bshift_nn(mb, (size_t)blockIdx.z * bstride);
   float2* __restrict__ out = mb->out;
   export_level(fl, wl * hl, mb);
   const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y * blockDim.y + threadIdx.y;

@@ -68,13 +68,13 @@ template <int P, bool L2, int NC>
 __global__ void __launch_bounds__(kPsThreads, (P == 12 && NC == 1) ? 512 / kPsThreads : 1) k_patch_search(const PatchSearchArgs a) {
   // batched handles: blockIdx.y = pair, all buffers of that pair sit a.g.bstride bytes further (common.cuh)
   const size_t boff = (size_t)blockIdx.y * a.g.bstride;
-  const float* __restrict__ pI0 = bshift(a.I0, boff);
-  const float* __restrict__ pI0x = bshift(a.I0x, boff);
-  const float* __restrict__ pI0y = bshift(a.I0y, boff);
-  const float* __restrict__ pI1 = bshift(a.I1, boff);
+  const float* __restrict__ pI0 = bshift_nn(a.I0, boff);
+  const float* __restrict__ pI0x = bshift_nn(a.I0x, boff);
+  const float* __restrict__ pI0y = bshift_nn(a.I0y, boff);
+  const float* __restrict__ pI1 = bshift_nn(a.I1, boff);
   const float2* __restrict__ pcoarse = bshift(a.flow_coarse, boff);
-  float2* __restrict__ ppflow = bshift(a.pflow, boff);
-  float* __restrict__ ppweight = bshift(a.pweight, boff);
+  float2* __restrict__ ppflow = bshift_nn(a.pflow, boff);
+  float* __restrict__ ppweight = bshift_nn(a.pweight, boff);
   constexpr int N = P * P * NC;
   constexpr int PW = P * NC;            // floats per patch row
   constexpr int NI = N / 8;             // chain length

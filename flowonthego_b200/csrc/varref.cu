@@ -63,8 +63,8 @@ __global__ void __launch_bounds__(256) k_warp(int w, int h, int pad, int pitch, 
   if (i >= w || j >= h) return;
   {  // blockIdx.z = pair of a batched handle (common.cuh)
     const size_t boff = (size_t)blockIdx.z * bstride;
-    I0 = bshift(I0, boff); I1 = bshift(I1, boff); flow = bshift(flow, boff);
-    avg = bshift(avg, boff); Iz = bshift(Iz, boff); mask = bshift(mask, boff);
+    I0 = bshift_nn(I0, boff); I1 = bshift_nn(I1, boff); flow = bshift_nn(flow, boff);
+    avg = bshift_nn(avg, boff); Iz = bshift_nn(Iz, boff); mask = bshift_nn(mask, boff);
   }
   const int o = j * w + i, n = w * h;
   const float2 f = flow[o];
@@ -131,8 +131,8 @@ __global__ void __launch_bounds__(256) k_deriv1(int w, int h, const float* __res
   const int o = j * w + i;
   {  // blockIdx.z = pair * noc + colour plane
     const size_t boff = (size_t)(blockIdx.z / noc) * bstride;
-    avg = bshift(avg, boff); Iz = bshift(Iz, boff); Ix = bshift(Ix, boff); Iy = bshift(Iy, boff);
-    Ixz = bshift(Ixz, boff); Iyz = bshift(Iyz, boff);
+    avg = bshift_nn(avg, boff); Iz = bshift_nn(Iz, boff); Ix = bshift_nn(Ix, boff); Iy = bshift_nn(Iy, boff);
+    Ixz = bshift_nn(Ixz, boff); Iyz = bshift_nn(Iyz, boff);
   }
   const size_t pl = (size_t)(blockIdx.z % noc) * w * h;  // colour plane
   avg += pl; Iz += pl; Ix += pl; Iy += pl; Ixz += pl; Iyz += pl;
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256) k_deriv2(int w, int h, const float* __res
   const int o = j * w + i;
   {  // blockIdx.z = pair * noc + colour plane
     const size_t boff = (size_t)(blockIdx.z / noc) * bstride;
-    Ix = bshift(Ix, boff); Iy = bshift(Iy, boff); Ixx = bshift(Ixx, boff); Ixy = bshift(Ixy, boff); Iyy = bshift(Iyy, boff);
+    Ix = bshift_nn(Ix, boff); Iy = bshift_nn(Iy, boff); Ixx = bshift_nn(Ixx, boff); Ixy = bshift_nn(Ixy, boff); Iyy = bshift_nn(Iyy, boff);
   }
   const size_t pl = (size_t)(blockIdx.z % noc) * w * h;  // colour plane
   Ix += pl; Iy += pl; Ixx += pl; Ixy += pl; Iyy += pl;
@@ -181,7 +181,8 @@ struct AssembleArgs {
   int noc;    // 1: single-channel data term; 3: RGB data term (planes of w*h floats)
   const float2* flow;  // wx, wy
   const float4* du4;   // (du,dv) records, wavefront-major
-  const float *mask, *Ix, *Iy, *Iz, *Ixx, *Ixy, *Iyy, *Ixz, *Iyz;
+  const float* stack;  // derivative stack + mask: array k at stack + k * astride (VarRefBuffers)
+  unsigned astride;
   float4 *coefA, *coefB;  // {a11,a12,a22,horiz}, {b1,b2,vert,0}, wavefront-major
   int* prog;              // SOR flags: [0] epoch, [1] ticket, [2..2+n_prog) per-item progress counters
   int n_prog;
@@ -212,12 +213,14 @@ __global__ void __launch_bounds__(ATX* ATY, 8) k_assemble(const AssembleArgs a_i
   AssembleArgs a = a_in;
   {
     const size_t boff = (size_t)blockIdx.z * a.bstride;
-    a.flow = bshift(a.flow, boff); a.du4 = bshift(a.du4, boff); a.mask = bshift(a.mask, boff);
-    a.Ix = bshift(a.Ix, boff); a.Iy = bshift(a.Iy, boff); a.Iz = bshift(a.Iz, boff);
-    a.Ixx = bshift(a.Ixx, boff); a.Ixy = bshift(a.Ixy, boff); a.Iyy = bshift(a.Iyy, boff);
-    a.Ixz = bshift(a.Ixz, boff); a.Iyz = bshift(a.Iyz, boff);
-    a.coefA = bshift(a.coefA, boff); a.coefB = bshift(a.coefB, boff); a.prog = bshift(a.prog, boff);
+    a.flow = bshift_nn(a.flow, boff); a.du4 = bshift_nn(a.du4, boff); a.stack = bshift_nn(a.stack, boff);
+    a.coefA = bshift_nn(a.coefA, boff); a.coefB = bshift_nn(a.coefB, boff); a.prog = bshift_nn(a.prog, boff);
   }
+  // array k of the derivative stack (written by k_warp / k_deriv1 / k_deriv2 of this level): 32-bit indices off one base
+  enum { S_IZ = 1, S_IX = 2, S_IY = 3, S_IXX = 4, S_IXY = 5, S_IYY = 6, S_IXZ = 7, S_IYZ = 8, S_MASK = 9 };
+  const float* __restrict__ S = a.stack;
+  const unsigned AS = a.astride;
+#define SP(k, idx) S[(unsigned)(k) * AS + (unsigned)(idx)]
   __shared__ float2 uu_s[ATY + 4][ATX + 4];
   __shared__ float2 du_s[ATY][ATX];
   __shared__ float s_s[ATY + 2][ATX + 2];
@@ -275,11 +278,11 @@ __global__ void __launch_bounds__(ATX* ATY, 8) k_assemble(const AssembleArgs a_i
 
     // compute_data (opticalflow_aux.c:310-438)
     const float du = du_s[ty][tx].x, dv = du_s[ty][tx].y;
-    const float mk = a.mask[o];
+    const float mk = SP(S_MASK, o);
     float A11 = 0.0f, A12 = 0.0f, A22 = 0.0f, B1 = 0.0f, B2 = 0.0f;
     if (a.noc == 1) {  // 1-channel branch
-      const float ix = a.Ix[o], iy = a.Iy[o], iz = a.Iz[o];
-      const float ixx = a.Ixx[o], ixy = a.Ixy[o], iyy = a.Iyy[o], ixz = a.Ixz[o], iyz = a.Iyz[o];
+      const float ix = SP(S_IX, o), iy = SP(S_IY, o), iz = SP(S_IZ, o);
+      const float ixx = SP(S_IXX, o), ixy = SP(S_IXY, o), iyy = SP(S_IYY, o), ixz = SP(S_IXZ, o), iyz = SP(S_IYZ, o);
       float tmp, tmp2, n1, n2;
       if (a.hd != 0.0f) {
         tmp = iz + ix * du + iy * dv;
@@ -310,19 +313,19 @@ __global__ void __launch_bounds__(ATX* ATY, 8) k_assemble(const AssembleArgs a_i
       B1 *= 3;
       B2 *= 3;
     } else {  // RGB branch: one robust weight over the three channels, no final x3
-      const size_t n = (size_t)w * h;
+      const unsigned n = (unsigned)(w * h);
       float t[6], nn[6], psi;
       if (a.hd != 0.0f) {
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
-          const float ix = a.Ix[ch * n + o], iy = a.Iy[ch * n + o], iz = a.Iz[ch * n + o];
+          const float ix = SP(S_IX, ch * n + o), iy = SP(S_IY, ch * n + o), iz = SP(S_IZ, ch * n + o);
           t[ch] = iz + ix * du + iy * dv;
           nn[ch] = ix * ix + iy * iy + kDnorm;
         }
         psi = mk * a.hd / sqrtf(t[0] * t[0] / nn[0] + t[1] * t[1] / nn[1] + t[2] * t[2] / nn[2] + kEps);
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
-          const float ix = a.Ix[ch * n + o], iy = a.Iy[ch * n + o], iz = a.Iz[ch * n + o];
+          const float ix = SP(S_IX, ch * n + o), iy = SP(S_IY, ch * n + o), iz = SP(S_IZ, ch * n + o);
           const float tc = psi / nn[ch];
           A11 += tc * ix * ix;
           A12 += tc * ix * iy;
@@ -333,18 +336,18 @@ __global__ void __launch_bounds__(ATX* ATY, 8) k_assemble(const AssembleArgs a_i
       }
 #pragma unroll
       for (int ch = 0; ch < 3; ++ch) {
-        const float ixx = a.Ixx[ch * n + o], ixy = a.Ixy[ch * n + o], iyy = a.Iyy[ch * n + o];
+        const float ixx = SP(S_IXX, ch * n + o), ixy = SP(S_IXY, ch * n + o), iyy = SP(S_IYY, ch * n + o);
         nn[2 * ch] = ixx * ixx + ixy * ixy + kDnorm;
         nn[2 * ch + 1] = iyy * iyy + ixy * ixy + kDnorm;
-        t[2 * ch] = a.Ixz[ch * n + o] + ixx * du + ixy * dv;
-        t[2 * ch + 1] = a.Iyz[ch * n + o] + ixy * du + iyy * dv;
+        t[2 * ch] = SP(S_IXZ, ch * n + o) + ixx * du + ixy * dv;
+        t[2 * ch + 1] = SP(S_IYZ, ch * n + o) + ixy * du + iyy * dv;
       }
       psi = mk * a.hg / sqrtf(t[0] * t[0] / nn[0] + t[1] * t[1] / nn[1] + t[2] * t[2] / nn[2] + t[3] * t[3] / nn[3] +
                               t[4] * t[4] / nn[4] + t[5] * t[5] / nn[5] + kEps);
 #pragma unroll
       for (int ch = 0; ch < 3; ++ch) {
-        const float ixx = a.Ixx[ch * n + o], ixy = a.Ixy[ch * n + o], iyy = a.Iyy[ch * n + o];
-        const float ixz = a.Ixz[ch * n + o], iyz = a.Iyz[ch * n + o];
+        const float ixx = SP(S_IXX, ch * n + o), ixy = SP(S_IXY, ch * n + o), iyy = SP(S_IYY, ch * n + o);
+        const float ixz = SP(S_IXZ, ch * n + o), iyz = SP(S_IYZ, ch * n + o);
         const float ta = psi / nn[2 * ch], tb = psi / nn[2 * ch + 1];
         A11 += ta * ixx * ixx + tb * ixy * ixy;
         A12 += ta * ixx * ixy + tb * ixy * iyy;
@@ -403,6 +406,7 @@ __global__ void __launch_bounds__(ATX* ATY, 8) k_assemble(const AssembleArgs a_i
     a.coefA[oc] = oa_s[ry][rx];
     a.coefB[oc] = ob_s[ry][rx];
   }
+#undef SP
 }
 
 // ---- sor_coupled: exact lexicographic sweeps as a skewed wavefront ------------------------------
@@ -744,8 +748,8 @@ __global__ void __launch_bounds__(256) k_update(int w, int h, float2* __restrict
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   if (i >= w || j >= h) return;
-  flow = bshift(flow, (size_t)blockIdx.z * bstride);
-  du4 = bshift(du4, (size_t)blockIdx.z * bstride);
+  flow = bshift_nn(flow, (size_t)blockIdx.z * bstride);
+  du4 = bshift_nn(du4, (size_t)blockIdx.z * bstride);
   const int o = j * w + i;
   const float2 f = flow[o];
   const float4 d = du4[Skew(w, h).at(i, j)];
@@ -799,8 +803,7 @@ int launch_varref(const LevelGeom& g, const VarParams& v, const float* I0, const
   cudaMemset2DAsync(b.du4, nb > 1 ? bs : sizeof(float4) * n_du4, 0, sizeof(float4) * n_du4, nb, st);
   for (int it = 0; it < v.n_inner; ++it) {
     AssembleArgs aa{w, h, v.qa, v.hg, v.hd, it == 0 ? 1 : 0, g.noc, flow, b.du4,
-                    b.mask, b.Ix, b.Iy, b.Iz, b.Ixx, b.Ixy, b.Iyy, b.Ixz, b.Iyz, b.coefA, b.coefB, b.progress,
-                    T * K, bs};
+                    b.stack, b.astride, b.coefA, b.coefB, b.progress, T * K, bs};
     {
       // smoothness 16 + data term 64 + sub_laplacian 32 + flow update 24 B/px
       ProfScope ps(prof, "k_assemble", g.lv, 136.0 * n);

@@ -156,3 +156,41 @@ def test_image_reader_rejects_malformed_files(tmp_path):
         with pytest.raises(F.DisError) as ei:
             F.read_image_gray(str(path))
         assert ei.value.code == 4, name  # DIS_ERR_IO
+
+
+def test_native_jpeg_decode_matches_opencv(tmp_path):
+    """Baseline JPEG -> grey: bit-identical to cv2.imread(.., IMREAD_GRAYSCALE) (libjpeg's luminance plane, islow IDCT)
+    for 4:2:0 / 4:4:4 / grey files, odd sizes, restart intervals; progressive files are refused.  The reference's own
+    fixtures images/road_HD.jpg and images/yosemite_4k.jpg are checked where the reference tree exists."""
+    import cv2
+    import flowonthego_b200 as F
+    from tests.synth import texture
+    rng = np.random.default_rng(5)
+    cases = []
+    for k, (w, h) in enumerate(((64, 48), (123, 77), (17, 9), (640, 360))):
+        col = np.stack([texture(w, h, 20 + 3 * k + c) for c in range(3)], -1)
+        col = np.clip(col.astype(int) + rng.integers(-20, 20, col.shape), 0, 255).astype(np.uint8)
+        for q in (35, 90):
+            cases.append(("c%d_q%d.jpg" % (k, q), col, [cv2.IMWRITE_JPEG_QUALITY, q]))
+        cases.append(("g%d.jpg" % k, col[..., 0].copy(), [cv2.IMWRITE_JPEG_QUALITY, 80]))
+        cases.append(("r%d.jpg" % k, col, [cv2.IMWRITE_JPEG_QUALITY, 75, cv2.IMWRITE_JPEG_RST_INTERVAL, 3]))
+        if hasattr(cv2, "IMWRITE_JPEG_SAMPLING_FACTOR"):
+            cases.append(("s444_%d.jpg" % k, col, [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444]))
+            cases.append(("s422_%d.jpg" % k, col, [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422]))
+    for name, img, flags in cases:
+        path = str(tmp_path / name)
+        assert cv2.imwrite(path, img, flags)
+        want = cv2.imread(path, cv2.IMREAD_GRAYSCALE)
+        got = F.read_image_gray(path)
+        assert got.shape == want.shape and np.array_equal(got, want), name
+    prog = str(tmp_path / "prog.jpg")
+    cv2.imwrite(prog, cases[0][1], [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
+    with pytest.raises(F.DisError):
+        F.read_image_gray(prog)
+    with pytest.raises(F.DisError):  # colour output from JPEG is not provided
+        F.read_image_bgr(str(tmp_path / cases[0][0]))
+    ref = os.environ.get("DIS_REFERENCE", "/root/reference")
+    for n in ("road_HD", "yosemite_4k"):
+        path = os.path.join(ref, "images", n + ".jpg")
+        if os.path.exists(path):
+            assert np.array_equal(F.read_image_gray(path), cv2.imread(path, cv2.IMREAD_GRAYSCALE)), n
