@@ -509,6 +509,7 @@ int enqueue_engine(dis_handle* h, const float2* d_initflow) {
   {  // auto: a fine level that fills the GPU by itself (4K at lv_l = 0) prefers the low-latency instantiation
     const LevelGeom& gfin = h->lv[q.lv_l].g;
     vp.sor_group = h->sor_group ? h->sor_group : ((size_t)gfin.w * gfin.h >= (1u << 20) ? 16 : 8);
+    vp.sor_full = h->sor_group == 16;  // asked for explicitly: the latency setting
   }
   Prof* prof = h->kprof_on ? &h->kprof : nullptr;
   // Tolerance mode: FMA-contracted builds of the search and the refinement.  Rounding differences grow with the

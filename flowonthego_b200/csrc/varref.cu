@@ -31,6 +31,7 @@
 // (16-byte {du,dv,tag} stores, no fences); successive sweeps chase each other through coarse
 // progress counters.  Items (sweep t, row block k) are handed out through a ticket in
 // dependency order, so a running warp only ever waits for warps that have already started.
+#include <algorithm>
 #include <type_traits>
 
 #include "common.cuh"
@@ -468,7 +469,7 @@ __device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
       : "memory");
 }
 
-template <int kG>
+template <int kG, bool kPersistent>
 __global__ void __launch_bounds__(32, kG == 8 ? 16 : 8) k_sor_wavefront(const SorArgs a_in) {
   constexpr int kCH = kG, kRD = 2 * kG;
   SorArgs a = a_in;
@@ -490,6 +491,18 @@ __global__ void __launch_bounds__(32, kG == 8 ? 16 : 8) k_sor_wavefront(const So
   const int w = a.w, h = a.h, T = a.T, K = a.K;
   const Skew sk(w, h);
   const int nsteps = sk.nsteps, nsp = sk.nsp;
+  // Persistent warp: the launch has only as many CTAs as items are busy at a time (launch_varref); a warp that has
+  // finished an item takes the next ticket.  Tickets are handed out in dependency order and a warp takes a new one
+  // only after finishing, so every item a running warp waits for is finished or running: no deadlock for any CTA
+  // count.  (With one CTA per item, two thirds of the resident warps only waited for their turn, holding their 25 KB.)
+  if (lane == 0) {
+    for (int q = 0; q < kNS; ++q) mbar_init(&bars[q], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  }
+  __syncwarp();
+  unsigned chunks_done = 0;  // chunks consumed by this warp so far: stage and phase parity of the coefficient ring
+  for (;;) {
   int tk = 0;
   if (lane == 0) tk = atomicAdd(a.prog + 1, 1);
   tk = __shfl_sync(FULL, tk, 0);
@@ -533,15 +546,11 @@ __global__ void __launch_bounds__(32, kG == 8 ? 16 : 8) k_sor_wavefront(const So
   const float omega = a.omega;
   const int nchunks = (nsteps + kCH - 1) / kCH;
 
-  // ---- coefficient streams: TMA bulk copies of kCH steps (8 KB per array) into a kNS-stage ring
-  if (lane == 0) {
-    for (int q = 0; q < kNS; ++q) mbar_init(&bars[q], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-  }
-  __syncwarp();
+  // ---- coefficient streams: TMA bulk copies of kCH steps (8 KB per array) into a kNS-stage ring; chunk c of this
+  // item is the warp's chunk number chunks_done + c
+  const unsigned c_base = chunks_done;
   auto tma_chunk = [&](int c) {  // lane 0 only
-    const int st = c % kNS;
+    const int st = (int)((c_base + (unsigned)c) % kNS);
     mbar_expect_tx(&bars[st], 2 * kCH * 512);
     tma_bulk_g2s(sA + (size_t)st * kCH * 512, gA + (size_t)c * kCH * 32, kCH * 512, &bars[st]);
     tma_bulk_g2s(sB + (size_t)st * kCH * 512, gB + (size_t)c * kCH * 32, kCH * 512, &bars[st]);
@@ -598,8 +607,8 @@ __global__ void __launch_bounds__(32, kG == 8 ? 16 : 8) k_sor_wavefront(const So
   const float tagf = __int_as_float(tag_cur);
 
   for (int c = 0; c < nchunks; ++c) {
-    const int st = c % kNS;
-    mbar_wait(&bars[st], (unsigned)(c / kNS) & 1u);
+    const int st = (int)((c_base + (unsigned)c) % kNS);
+    mbar_wait(&bars[st], ((c_base + (unsigned)c) / kNS) & 1u);
     const unsigned char* cA_p = sA + (size_t)st * kCH * 512 + lane * 16;
     const unsigned char* cB_p = sB + (size_t)st * kCH * 512 + lane * 16;
 #pragma unroll
@@ -740,6 +749,10 @@ __global__ void __launch_bounds__(32, kG == 8 ? 16 : 8) k_sor_wavefront(const So
     if (lane == 0 && c + kNS < nchunks) tma_chunk(c + kNS);
   }
   cp_async_wait<0>();
+  if (!kPersistent) return;  // one CTA per item (DIS_OPT_SOR_GROUP = 16 asked for explicitly: the latency setting)
+  chunks_done += (unsigned)nchunks;
+  __syncwarp();
+  }  // next ticket
 }
 
 // final flow = wx + du (refine_variational.cpp:212-221)
@@ -760,8 +773,9 @@ __global__ void __launch_bounds__(256) k_update(int w, int h, float2* __restrict
 
 // per-device opt-in to > 48 KB dynamic shared memory (called from dis_create on the handle's device)
 void varref_init_device() {
-  cudaFuncSetAttribute(k_sor_wavefront<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sor_smem<16>());
-  cudaFuncSetAttribute(k_sor_wavefront<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sor_smem<8>());
+  cudaFuncSetAttribute(k_sor_wavefront<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sor_smem<16>());
+  cudaFuncSetAttribute(k_sor_wavefront<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sor_smem<16>());
+  cudaFuncSetAttribute(k_sor_wavefront<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sor_smem<8>());
 }
 
 void varref_sizes(int w, int h, int n_solver, size_t* n_coef4, size_t* n_du4, size_t* n_prog) {
@@ -813,10 +827,16 @@ int launch_varref(const LevelGeom& g, const VarParams& v, const float* I0, const
     {
       // each sweep reads 9 arrays and writes 2: 44 B/px
       ProfScope ps(prof, "k_sor_wavefront", g.lv, 44.0 * T * n);
-      if (v.sor_group == 16)
-        k_sor_wavefront<16><<<dim3(T * K, nb), 32, sor_smem<16>(), st>>>(sa);
+      // CTAs = items busy at a time: total work (T K items of nsteps steps) over the critical path (section 4.4),
+      // plus slack; never more than one per item
+      const int lag = 80, path = sk.nsteps + (K - 1 + 2 * (T - 1)) * lag;
+      const int ctas = v.sor_full ? T * K : std::min(T * K, (int)(((long long)T * K * sk.nsteps + path - 1) / path) + 3);
+      if (v.sor_full)
+        k_sor_wavefront<16, false><<<dim3(ctas, nb), 32, sor_smem<16>(), st>>>(sa);
+      else if (v.sor_group == 16)
+        k_sor_wavefront<16, true><<<dim3(ctas, nb), 32, sor_smem<16>(), st>>>(sa);
       else
-        k_sor_wavefront<8><<<dim3(T * K, nb), 32, sor_smem<8>(), st>>>(sa);
+        k_sor_wavefront<8, true><<<dim3(ctas, nb), 32, sor_smem<8>(), st>>>(sa);
     }
     launches += 2;
   }

@@ -104,8 +104,9 @@ int dis_destroy(dis_handle* h);
 int dis_set_params(dis_handle* h, const dis_params* params);
 /* Execution options; none of the first three changes results.
  *   DIS_OPT_SOR_GROUP  8: smaller shared-memory footprint of the SOR wavefront kernel, best pairs/s when many
- *                      handles share the GPU; 16: lowest latency for a lone pair (about 7 % at 1080p); 0 (default):
- *                      16 when the finest processed level has >= 2^20 pixels (it fills the GPU alone), else 8.
+ *                      handles share the GPU; 16: lowest latency for a lone pair (about 10 % at 1080p: larger groups
+ *                      and one warp per (sweep, row block) item instead of persistent warps); 0 (default): persistent
+ *                      warps, groups of 16 when the finest processed level has >= 2^20 pixels, else of 8.
  *   DIS_OPT_USE_GRAPH  1 (default): record a run into a CUDA graph and replay it; 0: launch kernel by kernel.
  * DIS_OPT_LEVEL_OUTPUT changes WHAT dis_run_u8 / dis_submit_u8 copy back, not how it is computed: 1 = the engine's
  * own output as the OFC::OFClass constructor delivers it (level lv_l, (w_pad/2^lv_l) x (h_pad/2^lv_l) x 2 floats,
