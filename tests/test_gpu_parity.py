@@ -532,3 +532,31 @@ def test_two_processes_share_one_gpu(tmp_path):
     for s, pr in zip((31, 32), procs):
         out, err = pr.communicate(timeout=300)
         assert pr.returncode == 0 and out.strip() == "ok %d" % s, err[-2000:]
+
+
+def test_many_concurrent_handles_stay_bit_exact():
+    """Stress for the SOR hand-off (16-byte {du, dv, tag} records published without fences): many
+    handles run concurrently, so that wavefront warps of different pairs interleave on every SM; every result must still
+    be bit-identical to the oracle.  A torn record would show up as a differing (or non-deterministic) flow."""
+    import torch
+    w, h, n = 334, 210, 24
+    p = params(2, 1024, lv_f=3, lv_l=0, tv_solverit=5, tv_innerit=2)
+    pairs = [synth_pair(w, h, seed=70 + k)[:2] for k in range(4)]
+    refs = [port.run_u8(a, b, p.to_dict()) for a, b in pairs]
+    da = [torch.from_numpy(x[0]).cuda() for x in pairs]
+    db = [torch.from_numpy(x[1]).cuda() for x in pairs]
+    engines = [F.Engine(p, w, h) for _ in range(n)]
+    out = torch.zeros((n, h, w, 2), dtype=torch.float32, device="cuda")
+    try:
+        for rep in range(6):
+            for i, e in enumerate(engines):
+                k = (i + rep) % 4
+                e.submit_u8_device(da[k].data_ptr(), db[k].data_ptr(), w, h, w, out[i].data_ptr())
+            for i, e in enumerate(engines):
+                e.wait()
+            got = out.cpu().numpy()
+            for i in range(n):
+                assert bits_differ(got[i], refs[(i + rep) % 4]) == 0, (rep, i)
+    finally:
+        for e in engines:
+            e.close()
