@@ -19,7 +19,8 @@ def sor_ms(w, h, T, grp):
     return ms
 for grp in [int(x) for x in sys.argv[1:]] or (8, 16):
     base = None
-    for (w, h, T) in ((480, 32, 1), (960, 32, 1), (480, 64, 1), (480, 32, 2), (480, 32, 3), (480, 96, 1), (480, 288, 1), (480, 288, 3)):
+    for (w, h, T) in ((30, 17, 3), (60, 34, 3), (120, 68, 3), (240, 136, 3),  # the coarse levels of a 1080p pair
+                   (480, 32, 1), (960, 32, 1), (480, 64, 1), (480, 32, 2), (480, 32, 3), (480, 96, 1), (480, 288, 1), (480, 288, 3)):
         ms = sor_ms(w, h, T, grp)
         steps = w + 31
         print("G=%2d  %4dx%-3d T=%d  K=%d: %7.1f us  = %.0f cycles per step of one item" % (grp, w, h, T, (h + 31) // 32, ms * 1e3, ms * 1e-3 * 1.965e9 / steps), flush=True)
