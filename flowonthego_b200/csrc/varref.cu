@@ -2,8 +2,8 @@
 //
 // Replaces VarRefClass::VarRefClass / RefLevelOF (kroeger/refine_variational.cpp:25-116, 153-241)
 // and the FDF1.0.1 C kernels underneath:
-//   image_warp            kroeger/FDF1.0.1/opticalflow_aux.c:18-60      -> k_warp
-//   get_derivatives       opticalflow_aux.c:65-116, image.c:401-434,466-502 -> k_deriv1, k_deriv2
+//   image_warp            kroeger/FDF1.0.1/opticalflow_aux.c:18-60      -> k_front (stage A)
+//   get_derivatives       opticalflow_aux.c:65-116, image.c:401-434,466-502 -> k_front (stages B, C)
 //   compute_smoothness    opticalflow_aux.c:123-165, image.c:376-399,436-464 -> k_assemble
 //   compute_data          opticalflow_aux.c:310-438 (1-channel branch)        -> k_assemble
 //   sub_laplacian (x2)    opticalflow_aux.c:172-199                          -> k_assemble
@@ -52,42 +52,6 @@ constexpr float kEps = 0.001f * 0.001f;  // epsilon_color/grad/smooth, :11-14
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
-// ---- image_warp + first half of get_derivatives ------------------------------------------------
-// noc channels: the padded pyramid images are interleaved (copyimage de-interleaves them in the reference,
-// refine_variational.cpp:120-149); avg / Iz are written as noc planes of n = w*h floats; the mask is shared.
-__global__ void __launch_bounds__(256) k_warp(int w, int h, int pad, int pitch, int noc, const float* __restrict__ I0,
-                                              const float* __restrict__ I1, const float2* __restrict__ flow,
-                                              float* __restrict__ avg, float* __restrict__ Iz,
-                                              float* __restrict__ mask, size_t bstride) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = blockIdx.y * blockDim.y + threadIdx.y;
-  if (i >= w || j >= h) return;
-  {  // blockIdx.z = pair of a batched handle (common.cuh)
-    const size_t boff = (size_t)blockIdx.z * bstride;
-    I0 = bshift_nn(I0, boff); I1 = bshift_nn(I1, boff); flow = bshift_nn(flow, boff);
-    avg = bshift_nn(avg, boff); Iz = bshift_nn(Iz, boff); mask = bshift_nn(mask, boff);
-  }
-  const int o = j * w + i, n = w * h;
-  const float2 f = flow[o];
-  const float xx = (float)i + f.x, yy = (float)j + f.y;
-  const int x = (int)floorf(xx), y = (int)floorf(yy);
-  const float dx = xx - (float)x, dy = yy - (float)y;
-  const float m = (xx >= 0 && xx <= (float)(w - 1) && yy >= 0 && yy <= (float)(h - 1)) ? 1.0f : 0.0f;
-  const int x1 = clampi(x, 0, w - 1), x2 = clampi(x + 1, 0, w - 1);
-  const int y1 = clampi(y, 0, h - 1), y2 = clampi(y + 1, 0, h - 1);
-  const float* s = I1 + (size_t)pad * pitch + pad * noc;
-  for (int ch = 0; ch < noc; ++ch) {
-    const float s11 = __ldg(s + (size_t)y1 * pitch + x1 * noc + ch), s12 = __ldg(s + (size_t)y1 * pitch + x2 * noc + ch);
-    const float s21 = __ldg(s + (size_t)y2 * pitch + x1 * noc + ch), s22 = __ldg(s + (size_t)y2 * pitch + x2 * noc + ch);
-    const float wv = s11 * (1.0f - dx) * (1.0f - dy) + s12 * dx * (1.0f - dy) + s21 * (1.0f - dx) * dy +
-                     s22 * dx * dy;
-    const float i0 = __ldg(I0 + (size_t)(j + pad) * pitch + (i + pad) * noc + ch);
-    avg[(size_t)ch * n + o] = 0.5f * (wv + i0);
-    Iz[(size_t)ch * n + o] = wv - i0;
-  }
-  mask[o] = m;
-}
-
 // 5-tap derivative filter (refine_variational.cpp:45 + convolve_extract_coeffs image.c:339-342):
 // coeffs = {1/12, -8/12, -0, 8/12, -1/12}
 struct Cf5 {
@@ -102,63 +66,118 @@ __device__ __forceinline__ Cf5 cf5() {
   c.c4 = -(1.0f / 12.0f);
   return c;
 }
-// convolve_horiz_fast_5 (image.c:466-502): replicated border samples
-__device__ __forceinline__ float conv_h5(const float* __restrict__ s, int w, int i, int rowoff) {
-  const Cf5 c = cf5();
-  const float* r = s + rowoff;
-  return c.c0 * r[max(i - 2, 0)] + c.c1 * r[max(i - 1, 0)] + c.c2 * r[i] + c.c3 * r[min(i + 1, w - 1)] +
-         c.c4 * r[min(i + 2, w - 1)];
-}
-// convolve_vert_fast_5 (image.c:401-434): border rows use pre-summed coefficients
-__device__ __forceinline__ float conv_v5(const float* __restrict__ s, int w, int h, int i, int j) {
-  const Cf5 c = cf5();
-  const float* p = s + i;
-#define S(r) p[(size_t)(r)*w]
-  if (j == 0) return (c.c0 + c.c1 + c.c2) * S(0) + c.c3 * S(1) + c.c4 * S(2);
-  if (j == 1) return (c.c0 + c.c1) * S(0) + c.c2 * S(1) + c.c3 * S(2) + c.c4 * S(3);
-  if (j == h - 2) return c.c0 * S(j - 2) + c.c1 * S(j - 1) + c.c2 * S(j) + (c.c3 + c.c4) * S(j + 1);
-  if (j == h - 1) return c.c0 * S(j - 2) + c.c1 * S(j - 1) + (c.c2 + c.c3 + c.c4) * S(j);
-  return c.c0 * S(j - 2) + c.c1 * S(j - 1) + c.c2 * S(j) + c.c3 * S(j + 1) + c.c4 * S(j + 2);
-#undef S
-}
+// ---- fused, shared-memory-tiled front end: image_warp + both passes of get_derivatives in one kernel -----------------
+// Tile of FTX x FTY pixels per block.  Stage A warps I1 and forms avg = 0.5 (I1w + I0), Iz = I1w - I0 on the tile plus
+// a halo of 4 in shared memory; stage B takes the 5-tap derivatives Ix, Iy of avg on the tile plus a halo of 2 (shared)
+// and Ixz, Iyz of Iz on the tile (global); stage C the second derivatives Ixx, Ixy = d/dy Ix, Iyy on the tile.  avg
+// never leaves the SM.  noc channels: the padded pyramid images are interleaved (copyimage de-interleaves them in the
+// reference, refine_variational.cpp:120-149); the stack holds noc planes of n = w*h floats per array, the mask one.
+// Every value is produced by the reference's expression from the same operands -- the horizontal filter replicates border samples by clamping the index, the vertical one
+// uses the reference's pre-summed border coefficients on the image's first / last two rows -- so the planes are
+// bit-identical; samples outside the image are never read.
+constexpr int FTX = 32, FTY = 16;
+struct FrontArgs {
+  int w, h, pad, pitch, noc;
+  const float *I0, *I1;
+  const float2* flow;
+  float* stack;  // derivative stack + mask (VarRefBuffers): array k at stack + k * astride
+  unsigned astride;
+  size_t bstride;
+};
 
-__global__ void __launch_bounds__(256) k_deriv1(int w, int h, const float* __restrict__ avg,
-                                                const float* __restrict__ Iz, float* __restrict__ Ix,
-                                                float* __restrict__ Iy, float* __restrict__ Ixz,
-                                                float* __restrict__ Iyz, int noc, size_t bstride) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = blockIdx.y * blockDim.y + threadIdx.y;
-  if (i >= w || j >= h) return;
-  const int o = j * w + i;
-  {  // blockIdx.z = pair * noc + colour plane
-    const size_t boff = (size_t)(blockIdx.z / noc) * bstride;
-    avg = bshift_nn(avg, boff); Iz = bshift_nn(Iz, boff); Ix = bshift_nn(Ix, boff); Iy = bshift_nn(Iy, boff);
-    Ixz = bshift_nn(Ixz, boff); Iyz = bshift_nn(Iyz, boff);
+__global__ void __launch_bounds__(256) k_front(const FrontArgs a) {
+  enum { S_IZ = 1, S_IX = 2, S_IY = 3, S_IXX = 4, S_IXY = 5, S_IYY = 6, S_IXZ = 7, S_IYZ = 8, S_MASK = 9 };
+  __shared__ float avg_s[FTY + 8][FTX + 8], iz_s[FTY + 8][FTX + 8];
+  __shared__ float ix_s[FTY + 4][FTX + 4], iy_s[FTY + 4][FTX + 4];
+  const size_t boff = (size_t)blockIdx.z * a.bstride;
+  const float* __restrict__ I0 = bshift_nn(a.I0, boff);
+  const float* __restrict__ I1 = bshift_nn(a.I1, boff);
+  const float2* __restrict__ flow = bshift_nn(a.flow, boff);
+  float* __restrict__ S = bshift_nn(a.stack, boff);
+  const unsigned AS = a.astride;
+  const int w = a.w, h = a.h, pad = a.pad, pitch = a.pitch, noc = a.noc, n = w * h;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int i0 = blockIdx.x * FTX, j0 = blockIdx.y * FTY;
+  const Cf5 c = cf5();
+  const float* s1 = I1 + (size_t)pad * pitch + pad * noc;
+  for (int ch = 0; ch < noc; ++ch) {
+    // ---- stage A: warp (opticalflow_aux.c:18-60) and avg / Iz (:70-71) on the tile + halo 4
+    for (int q = tid; q < (FTY + 8) * (FTX + 8); q += 256) {
+      const int ly = q / (FTX + 8), lx = q - ly * (FTX + 8);
+      const int i = i0 + lx - 4, j = j0 + ly - 4;
+      if (i < 0 || i >= w || j < 0 || j >= h) continue;
+      const int o = j * w + i;
+      const float2 f = flow[o];
+      const float xx = (float)i + f.x, yy = (float)j + f.y;
+      const int x = (int)floorf(xx), y = (int)floorf(yy);
+      const float dx = xx - (float)x, dy = yy - (float)y;
+      const int x1 = clampi(x, 0, w - 1), x2 = clampi(x + 1, 0, w - 1);
+      const int y1 = clampi(y, 0, h - 1), y2 = clampi(y + 1, 0, h - 1);
+      const float s11 = __ldg(s1 + (size_t)y1 * pitch + x1 * noc + ch), s12 = __ldg(s1 + (size_t)y1 * pitch + x2 * noc + ch);
+      const float s21 = __ldg(s1 + (size_t)y2 * pitch + x1 * noc + ch), s22 = __ldg(s1 + (size_t)y2 * pitch + x2 * noc + ch);
+      const float wv = s11 * (1.0f - dx) * (1.0f - dy) + s12 * dx * (1.0f - dy) + s21 * (1.0f - dx) * dy +
+                       s22 * dx * dy;
+      const float v0 = __ldg(I0 + (size_t)(j + pad) * pitch + (i + pad) * noc + ch);
+      avg_s[ly][lx] = 0.5f * (wv + v0);
+      const float iz = wv - v0;
+      iz_s[ly][lx] = iz;
+      if (lx >= 4 && lx < FTX + 4 && ly >= 4 && ly < FTY + 4) {  // the tile itself
+        S[S_IZ * AS + (unsigned)(ch * n + o)] = iz;
+        if (ch == 0) S[S_MASK * AS + (unsigned)o] = (xx >= 0 && xx <= (float)(w - 1) && yy >= 0 && yy <= (float)(h - 1)) ? 1.0f : 0.0f;
+      }
+    }
+    __syncthreads();
+    // 5-tap filters on a shared tile whose element (ly, lx) is image pixel (j0 + ly - H, i0 + lx - H)
+    auto hconv = [&](const float* row, int i, int H) {  // convolve_horiz_fast_5 (image.c:466-502)
+      const int b = i0 - H;
+      return c.c0 * row[max(i - 2, 0) - b] + c.c1 * row[max(i - 1, 0) - b] + c.c2 * row[i - b] + c.c3 * row[min(i + 1, w - 1) - b] +
+             c.c4 * row[min(i + 2, w - 1) - b];
+    };
+    // ---- stage B: Ix, Iy of avg on the tile + halo 2; Ixz, Iyz of Iz on the tile
+    for (int q = tid; q < (FTY + 4) * (FTX + 4); q += 256) {
+      const int ly = q / (FTX + 4), lx = q - ly * (FTX + 4);
+      const int i = i0 + lx - 2, j = j0 + ly - 2;
+      if (i < 0 || i >= w || j < 0 || j >= h) continue;
+      const int ay = ly + 2, ax = lx + 2;  // the same pixel in the halo-4 tiles
+#define V5(T_, X_)                                                                                                      \
+  (j == 0       ? (c.c0 + c.c1 + c.c2) * T_[ay][X_] + c.c3 * T_[ay + 1][X_] + c.c4 * T_[ay + 2][X_]                                 \
+   : j == 1     ? (c.c0 + c.c1) * T_[ay - 1][X_] + c.c2 * T_[ay][X_] + c.c3 * T_[ay + 1][X_] + c.c4 * T_[ay + 2][X_]                  \
+   : j == h - 2 ? c.c0 * T_[ay - 2][X_] + c.c1 * T_[ay - 1][X_] + c.c2 * T_[ay][X_] + (c.c3 + c.c4) * T_[ay + 1][X_]                  \
+   : j == h - 1 ? c.c0 * T_[ay - 2][X_] + c.c1 * T_[ay - 1][X_] + (c.c2 + c.c3 + c.c4) * T_[ay][X_]                                 \
+                : c.c0 * T_[ay - 2][X_] + c.c1 * T_[ay - 1][X_] + c.c2 * T_[ay][X_] + c.c3 * T_[ay + 1][X_] + c.c4 * T_[ay + 2][X_])
+      const float ix = hconv(avg_s[ay], i, 4), iy = V5(avg_s, ax);
+      ix_s[ly][lx] = ix;
+      iy_s[ly][lx] = iy;
+      if (lx >= 2 && lx < FTX + 2 && ly >= 2 && ly < FTY + 2) {
+        const unsigned o = (unsigned)(ch * n + j * w + i);
+        S[S_IX * AS + o] = ix;
+        S[S_IY * AS + o] = iy;
+        S[S_IXZ * AS + o] = hconv(iz_s[ay], i, 4);
+        S[S_IYZ * AS + o] = V5(iz_s, ax);
+      }
+#undef V5
+    }
+    __syncthreads();
+    // ---- stage C: second derivatives on the tile
+    for (int q = tid; q < FTY * FTX; q += 256) {
+      const int ty = q / FTX, tx = q - ty * FTX;
+      const int i = i0 + tx, j = j0 + ty;
+      if (i >= w || j >= h) continue;
+      const int ay = ty + 2, ax = tx + 2;
+#define V5(T_, X_)                                                                                                      \
+  (j == 0       ? (c.c0 + c.c1 + c.c2) * T_[ay][X_] + c.c3 * T_[ay + 1][X_] + c.c4 * T_[ay + 2][X_]                                 \
+   : j == 1     ? (c.c0 + c.c1) * T_[ay - 1][X_] + c.c2 * T_[ay][X_] + c.c3 * T_[ay + 1][X_] + c.c4 * T_[ay + 2][X_]                  \
+   : j == h - 2 ? c.c0 * T_[ay - 2][X_] + c.c1 * T_[ay - 1][X_] + c.c2 * T_[ay][X_] + (c.c3 + c.c4) * T_[ay + 1][X_]                  \
+   : j == h - 1 ? c.c0 * T_[ay - 2][X_] + c.c1 * T_[ay - 1][X_] + (c.c2 + c.c3 + c.c4) * T_[ay][X_]                                 \
+                : c.c0 * T_[ay - 2][X_] + c.c1 * T_[ay - 1][X_] + c.c2 * T_[ay][X_] + c.c3 * T_[ay + 1][X_] + c.c4 * T_[ay + 2][X_])
+      const unsigned o = (unsigned)(ch * n + j * w + i);
+      S[S_IXX * AS + o] = hconv(ix_s[ay], i, 2);
+      S[S_IXY * AS + o] = V5(ix_s, ax);
+      S[S_IYY * AS + o] = V5(iy_s, ax);
+#undef V5
+    }
+    __syncthreads();
   }
-  const size_t pl = (size_t)(blockIdx.z % noc) * w * h;  // colour plane
-  avg += pl; Iz += pl; Ix += pl; Iy += pl; Ixz += pl; Iyz += pl;
-  Ix[o] = conv_h5(avg, w, i, j * w);
-  Iy[o] = conv_v5(avg, w, h, i, j);
-  Ixz[o] = conv_h5(Iz, w, i, j * w);
-  Iyz[o] = conv_v5(Iz, w, h, i, j);
-}
-
-__global__ void __launch_bounds__(256) k_deriv2(int w, int h, const float* __restrict__ Ix,
-                                                const float* __restrict__ Iy, float* __restrict__ Ixx,
-                                                float* __restrict__ Ixy, float* __restrict__ Iyy, int noc, size_t bstride) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = blockIdx.y * blockDim.y + threadIdx.y;
-  if (i >= w || j >= h) return;
-  const int o = j * w + i;
-  {  // blockIdx.z = pair * noc + colour plane
-    const size_t boff = (size_t)(blockIdx.z / noc) * bstride;
-    Ix = bshift_nn(Ix, boff); Iy = bshift_nn(Iy, boff); Ixx = bshift_nn(Ixx, boff); Ixy = bshift_nn(Ixy, boff); Iyy = bshift_nn(Iyy, boff);
-  }
-  const size_t pl = (size_t)(blockIdx.z % noc) * w * h;  // colour plane
-  Ix += pl; Iy += pl; Ixx += pl; Ixy += pl; Iyy += pl;
-  Ixx[o] = conv_h5(Ix, w, i, j * w);
-  Ixy[o] = conv_v5(Ix, w, h, i, j);
-  Iyy[o] = conv_v5(Iy, w, h, i, j);
 }
 
 // ---- one inner fixed-point iteration: smoothness + data term + Laplacian RHS + block inverse ----
@@ -217,7 +236,7 @@ __global__ void __launch_bounds__(ATX* ATY, 8) k_assemble(const AssembleArgs a_i
     a.flow = bshift_nn(a.flow, boff); a.du4 = bshift_nn(a.du4, boff); a.stack = bshift_nn(a.stack, boff);
     a.coefA = bshift_nn(a.coefA, boff); a.coefB = bshift_nn(a.coefB, boff); a.prog = bshift_nn(a.prog, boff);
   }
-  // array k of the derivative stack (written by k_warp / k_deriv1 / k_deriv2 of this level): 32-bit indices off one base
+  // array k of the derivative stack (written by k_front of this level): 32-bit indices off one base
   enum { S_IZ = 1, S_IX = 2, S_IY = 3, S_IXX = 4, S_IXY = 5, S_IYY = 6, S_IXZ = 7, S_IYZ = 8, S_MASK = 9 };
   const float* __restrict__ S = a.stack;
   const unsigned AS = a.astride;
@@ -796,18 +815,12 @@ int launch_varref(const LevelGeom& g, const VarParams& v, const float* I0, const
   dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8, nb);
   // algorithmic bytes per SURVEY.md section 8(d): warp+mask 28 B/px, derivative stack 40 B/px
   {
-    ProfScope ps(prof, "k_warp", g.lv, 28.0 * n);
-    k_warp<<<grid, block, 0, st>>>(w, h, g.pad, g.pitch, g.noc, I0, I1, flow, b.avg, b.Iz, b.mask, bs);
+    ProfScope ps(prof, "k_front", g.lv, 68.0 * n);
+    FrontArgs fa{w, h, g.pad, g.pitch, g.noc, I0, I1, flow, b.stack, b.astride, bs};
+    k_front<<<dim3((w + FTX - 1) / FTX, (h + FTY - 1) / FTY, nb), dim3(32, 8), 0, st>>>(fa);
   }
-  {
-    ProfScope ps(prof, "k_deriv1", g.lv, 24.0 * n);
-    k_deriv1<<<dim3(grid.x, grid.y, g.noc * nb), block, 0, st>>>(w, h, b.avg, b.Iz, b.Ix, b.Iy, b.Ixz, b.Iyz, g.noc, bs);
-  }
-  {
-    ProfScope ps(prof, "k_deriv2", g.lv, 16.0 * n);
-    k_deriv2<<<dim3(grid.x, grid.y, g.noc * nb), block, 0, st>>>(w, h, b.Ix, b.Iy, b.Ixx, b.Ixy, b.Iyy, g.noc, bs);
-  }
-  launches += 3;
+  launches += 1;
+
   if (v.n_inner <= 0) return launches;
   const Skew sk(w, h);
   const int K = sk.K, T = v.n_solver;
