@@ -189,7 +189,7 @@ def pinned_empty(shape, dtype):
 _PINNED = {}
 
 
-OPT_SOR_GROUP, OPT_USE_GRAPH, OPT_LEVEL_OUTPUT, OPT_ARITH = 1, 2, 3, 4
+OPT_SOR_GROUP, OPT_USE_GRAPH, OPT_LEVEL_OUTPUT, OPT_ARITH, OPT_SOR_SMALL = 1, 2, 3, 4, 5
 
 
 class Engine:
@@ -229,7 +229,7 @@ class Engine:
         _check(lib().dis_set_params(self._h, ctypes.byref(self.params)), self._h)
 
     def set_option(self, option, value):
-        """OPT_SOR_GROUP (8 | 16), OPT_USE_GRAPH (0 | 1), OPT_LEVEL_OUTPUT: results never change.
+        """OPT_SOR_GROUP (8 | 16), OPT_SOR_SMALL (0 ... 9), OPT_USE_GRAPH (0 | 1), OPT_LEVEL_OUTPUT: results never change.
         OPT_ARITH (0 exact | 1 tolerance mode, FMA contraction; maxiter <= 32 only) does change them."""
         _check(lib().dis_set_option(self._h, int(option), int(value)), self._h)
         if int(option) == OPT_LEVEL_OUTPUT:

@@ -53,6 +53,7 @@ struct VarParams {  // kroeger/refine_variational.cpp:28-42
   float qa, hg, hd, omega;
   int n_inner, n_solver;
   int sor_group;  // 8 or 16: k_sor_wavefront instantiation (DIS_OPT_SOR_GROUP)
+  int sor_small;  // levels of at most this many 32-row blocks take the one-CTA k_sor_small (DIS_OPT_SOR_SMALL)
   int sor_full;   // 1: one CTA per (sweep, row block) item -- lowest latency for a lone pair; 0: only as many CTAs as
                   // items are busy at a time, each warp taking ticket after ticket (best pairs/s)
 };

@@ -130,6 +130,7 @@ struct dis_handle {
   // graph
   bool use_graph = true;
   int sor_group = 0;  // DIS_OPT_SOR_GROUP: 0 auto, 8, 16
+  int sor_small = -1;  // DIS_OPT_SOR_SMALL: row blocks (of 32 rows) up to which a level takes the one-CTA SOR; -1 auto
   bool level_output = false;  // DIS_OPT_LEVEL_OUTPUT
   bool arith_fast = false;    // DIS_OPT_ARITH
   float2* lvl_export[kMaxBatch] = {};  // dis_set_level_export: per pair, device target of the level-lv_l flow (or null)
@@ -510,6 +511,7 @@ int enqueue_engine(dis_handle* h, const float2* d_initflow) {
     const LevelGeom& gfin = h->lv[q.lv_l].g;
     vp.sor_group = h->sor_group ? h->sor_group : ((size_t)gfin.w * gfin.h >= (1u << 20) ? 16 : 8);
     vp.sor_full = h->sor_group == 16;  // asked for explicitly: the latency setting
+    vp.sor_small = h->sor_small >= 0 ? h->sor_small : (vp.sor_full ? 4 : 5);  // measured: latency / throughput optimum at 1080p
   }
   Prof* prof = h->kprof_on ? &h->kprof : nullptr;
   // Tolerance mode: FMA-contracted builds of the search and the refinement.  Rounding differences grow with the
@@ -923,6 +925,15 @@ int dis_set_option(dis_handle* h, int option, int value) {
         CU(h, cudaStreamSynchronize(h->stream));
         drop_graph(h);
         h->sor_group = value;
+      }
+      return DIS_OK;
+    case DIS_OPT_SOR_SMALL:
+      if (value < -1 || value > 9) return fail(h, DIS_ERR_INVALID_ARG, "DIS_OPT_SOR_SMALL must be -1 (auto) or 0 ... 9 (row blocks of 32 rows)");
+      if (value != h->sor_small) {
+        CU(h, cudaSetDevice(h->device));
+        CU(h, cudaStreamSynchronize(h->stream));
+        drop_graph(h);
+        h->sor_small = value;
       }
       return DIS_OK;
     case DIS_OPT_LEVEL_OUTPUT:

@@ -181,16 +181,16 @@ __global__ void __launch_bounds__(256) k_front(const FrontArgs a) {
 }
 
 // ---- one inner fixed-point iteration: smoothness + data term + Laplacian RHS + block inverse ----
-constexpr int SK = 1;  // wavefront skew (columns per row)
+constexpr int SK = 1;  // wavefront skew (columns per row) of k_sor_wavefront; levels that take k_sor_small use 2
 
 // wavefront-major addressing of one level
 struct Skew {
-  int w, h, K, nsteps, nsp;  // nsp: steps per row block as allocated (whole TMA chunks + prefetch overrun)
-  __host__ __device__ Skew(int w_, int h_)
-      : w(w_), h(h_), K((h_ + 31) / 32), nsteps(w_ + SK * 31), nsp((w_ + SK * 31 + 15) / 16 * 16 + 32) {}
+  int w, h, K, sk, nsteps, nsp;  // sk: columns per row; nsp: steps per row block as allocated (whole TMA chunks + prefetch overrun)
+  __host__ __device__ Skew(int w_, int h_, int sk_ = SK)
+      : w(w_), h(h_), K((h_ + 31) / 32), sk(sk_), nsteps(w_ + sk_ * 31), nsp((w_ + sk_ * 31 + 15) / 16 * 16 + 32) {}
   __host__ __device__ size_t at(int i, int j) const {  // float4 index of pixel (i,j)
     const int k = j >> 5, l = j & 31;
-    return ((size_t)k * nsp + i + SK * l) * 32 + l;
+    return ((size_t)k * nsp + i + sk * l) * 32 + l;
   }
 };
 
@@ -206,6 +206,7 @@ struct AssembleArgs {
   float4 *coefA, *coefB;  // {a11,a12,a22,horiz}, {b1,b2,vert,0}, wavefront-major
   int* prog;              // SOR flags: [0] epoch, [1] ticket, [2..2+n_prog) per-item progress counters
   int n_prog;
+  int skew;               // columns per row of the wavefront-major layout (Skew::sk)
   size_t bstride;         // batched handles: blockIdx.z = pair
 };
 
@@ -215,7 +216,7 @@ __device__ __forceinline__ float2 uu_at(const AssembleArgs& a, int i, int j, flo
     *d_out = make_float2(0.0f, 0.0f);
     return f;
   }
-  const float4 d = a.du4[Skew(a.w, a.h).at(i, j)];
+  const float4 d = a.du4[Skew(a.w, a.h, a.skew).at(i, j)];
   *d_out = make_float2(d.x, d.y);
   return make_float2(f.x + d.x, f.y + d.y);  // refine_variational.cpp:212-213
 }
@@ -414,11 +415,11 @@ __global__ void __launch_bounds__(ATX* ATY, 8) k_assemble(const AssembleArgs a_i
     ob_s[ty][tx] = make_float4(B1, B2, vb, 0.0f);
   }
   __syncthreads();
-  // ---- phase 4: wavefront-major stores.  Pixels of this tile with equal tx + ty share one SOR step; their
+  // ---- phase 4: wavefront-major stores.  Pixels of this tile with equal tx + skew * ty share one SOR step; their
   // 8 lanes (rows j0..j0+7 of one 32-row block) are contiguous in the [step][lane] layout.
-  const Skew sk(w, h);
-  for (int q = tid; q < (ATX + ATY - 1) * ATY; q += ATX * ATY) {
-    const int sd = q / ATY, ry = q - sd * ATY, rx = sd - ry;
+  const Skew sk(w, h, a.skew);
+  for (int q = tid; q < (ATX + a.skew * (ATY - 1)) * ATY; q += ATX * ATY) {
+    const int sd = q / ATY, ry = q - sd * ATY, rx = sd - a.skew * ry;
     if (rx < 0 || rx >= ATX) continue;
     const int gi = i0 + rx, gj = j0 + ry;
     if (gi >= w || gj >= h) continue;
@@ -774,9 +775,245 @@ __global__ void __launch_bounds__(32, kG == 8 ? 16 : 8) k_sor_wavefront(const So
   }  // next ticket
 }
 
+// ---- the SOR of a small level: ONE CTA per pair, one warp per (sweep, row block), one barrier per step ------------
+// Thread (s, j) owns image row j in sweep s (32 rows per warp = the row blocks of the wavefront-major layout).  At
+// step t it updates the C pixels (i0 ... i0 + C - 1, j), i0 = C (t - j - 2 s): the lexicographic Gauss-Seidel order
+// of sor_coupled only asks that (i-1, j) and (i, j-1) of the same sweep and (i+1, j), (i, j+1) of the previous sweep
+// are final; with rows C columns apart and sweeps two steps apart all of them were produced at step t - 1 or by the
+// thread itself.  The whole launch is w / C + h - 1 + 2 (T - 1) steps -- the wavefront kernel's pipeline of (sweep, row
+// block) items needs a lag of 2 kG + 2 steps per sweep and ~54 per row block, which is most of its
+// time on a coarse level.  Every thread publishes its pixels of the step in a double-buffered shared array
+// res[parity][s][j][C]; neighbours read it after the step's barrier.  Levels that take this kernel use the
+// wavefront-major layout with a skew of C columns per row (Skew::sk), so that the C columns of a step are C whole
+// wavefront steps of the layout: the coefficient streams (and, for sweep 0, the du records of the previous launch)
+// arrive in shared rings of wavefront steps filled by cp.async D steps ahead, 512 contiguous bytes per warp, array and
+// wavefront step, the three arrays shared out over the sweeps' warps; only the last sweep writes records.  A warp
+// whose rows are all outside the image columns at a step only publishes zeros.  Arithmetic per pixel: that of
+// k_sor_wavefront, same order.  Measured (profiles/README.md): a step costs ~250 cycles + ~110 per pixel, so C = 2.
+constexpr size_t kSorSmallMaxSmem = 200 * 1024;
+constexpr int kSmallC = 2;  // columns per step (template parameter C of k_sor_small; 1, 2 and 4 work)
+
+__device__ __forceinline__ float4 lds128(unsigned a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float2 lds64(unsigned a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];\n" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds32(unsigned a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+template <int C>
+struct SorSmallDist {
+  static constexpr int value = C == 4 ? 3 : C == 2 ? 4 : 8;  // prefetch distance in steps
+};
+template <int C>
+inline size_t sor_small_smem(int rows, int T) {
+  constexpr int D = SorSmallDist<C>::value;
+  return (size_t)rows * C * ((D + 2 * T) * 32 + D * 8 + 2 * T * 8);
+}
+
+template <int C>
+__global__ void __launch_bounds__(512) k_sor_small(const SorArgs a_in, const int first) {
+  constexpr int D = SorSmallDist<C>::value;
+  SorArgs a = a_in;
+  {
+    const size_t boff = (size_t)blockIdx.x * a.bstride;
+    a.coefA = bshift_nn(a.coefA, boff); a.coefB = bshift_nn(a.coefB, boff); a.du4 = bshift_nn(a.du4, boff);
+  }
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int w = a.w, h = a.h, T = a.T, K = a.K;
+  const int rows = K * 32;
+  const int s = (int)(threadIdx.x >> 5) / K, k = (int)(threadIdx.x >> 5) - s * K, l = threadIdx.x & 31, j = k * 32 + l;
+  // shared memory (byte offsets).  One slot = one wavefront step of the layout = one column of every row:
+  // rA [C (D + 2 T)][rows] float4 {inverse block a11 a12 a22, horiz} | rB likewise {b1, b2, vert, -} |
+  // rD [C D][rows] float2 du, dv before this launch | rR [2][T][rows][C] float2 results of the previous step
+  unsigned sb = smem_u32(smem_raw);
+  asm volatile("" : "+r"(sb));  // keep it in a register (the compiler would re-derive it from %cluster_ctaid every step)
+  const unsigned strideA = (unsigned)rows * 16, ringA = (unsigned)(C * (D + 2 * T)) * strideA;
+  const unsigned strideD = (unsigned)rows * 8, ringD = (unsigned)(C * D) * strideD;
+  const unsigned offB = ringA, offD = 2 * ringA, offR = offD + ringD, resHalf = (unsigned)(T * rows) * (C * 8);
+  const Skew sk(w, h, C);
+  const int nsteps = sk.nsteps;
+  const size_t blk = ((size_t)k * sk.nsp) * 32 + l;
+  const float omega = a.omega;
+  {
+    float2* const z = reinterpret_cast<float2*>(smem_raw + offD);  // du = dv = 0 (first iteration) and no results yet
+    for (int q = threadIdx.x; q < C * D * rows + 2 * T * rows * C; q += blockDim.x) z[q] = make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  // Fetch duty: per step the C wavefront steps u .. u + C - 1 of the layout (columns u - C j ... of row j) = steps
+  // u - 32 C k of a row block, 512 contiguous bytes per array, row block and wavefront step.  The three arrays are
+  // shared out over the sweeps' warps of a row block: array q (coefA, coefB, du records) goes to sweep q mod T.
+  const bool f_a = (0 % T) == s, f_b = (1 % T) == s, f_d = (2 % T) == s && !first;
+  const float4* fA = a.coefA + blk - (ptrdiff_t)(32 * C * k) * 32;
+  const float4* fB = a.coefB + blk - (ptrdiff_t)(32 * C * k) * 32;
+  const float4* fD = a.du4 + blk - (ptrdiff_t)(32 * C * k) * 32;
+  int fsp = -32 * C * k;
+  unsigned fo = 0, fod = 0;
+  auto fetch = [&]() {
+#pragma unroll
+    for (int q = 0; q < C; ++q)
+      if ((unsigned)(fsp + q) < (unsigned)nsteps) {
+        const unsigned d = sb + fo + q * strideA + j * 16;
+        if (f_a) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(fA + q * 32) : "memory");
+        if (f_b) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d + offB), "l"(fB + q * 32) : "memory");
+        if (f_d) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sb + offD + fod + q * strideD + j * 8), "l"(fD + q * 32) : "memory");
+      }
+    cp_async_commit();
+    fA += 32 * C; fB += 32 * C; fD += 32 * C;
+    fsp += C;
+    fo += C * strideA;
+    fo = (fo == ringA) ? 0u : fo;
+    fod += C * strideD;
+    fod = (fod == ringD) ? 0u : fod;
+  };
+  for (int u = 0; u < D; ++u) fetch();
+  cp_async_wait<D - 2>();  // steps 0 and 1 have landed
+  __syncthreads();
+
+  const bool no_up = (j == 0), no_dn = (j >= h - 1), row_ok = j < h, last = (s == T - 1);
+  const int jp = max(j - 1, 0), jn = min(j + 1, rows - 1);
+  // per-thread addresses; the ring slots of step t - 2 s advance by C strideA per step, the result buffers alternate
+  const unsigned aSelf = sb + j * 16, aVt = sb + offB + jp * 16 + 8;
+  const unsigned aUp = sb + offR + (unsigned)(s * rows + jp) * (C * 8), aOut = sb + offR + (unsigned)(s * rows + j) * (C * 8);
+  const unsigned aOld = s == 0 ? sb + offD + j * 8 : sb + offR + (unsigned)((s - 1) * rows + j) * (C * 8);
+  const unsigned aBel = s == 0 ? sb + offD + jn * 8 : sb + offR + (unsigned)((s - 1) * rows + jn) * (C * 8);
+  const int RS = D + 2 * T;                                          // steps the coefficient ring holds
+  unsigned o = (unsigned)(((-2 * s) % RS + RS) % RS) * C * strideA;      // slots of step t - 2 s: columns i0 ... i0 + C - 1
+  unsigned om = (unsigned)(((-2 * s - 1) % RS + RS) % RS) * C * strideA;  // the step before: the row above at these columns
+  unsigned od = (D > 1 ? 1u : 0u) * C * strideD;                     // sweep 0: slots of step t + 1 in the du ring
+  unsigned pc = 0;                                                   // byte offset of this step's result buffer
+  float2 res1 = make_float2(0.f, 0.f);  // my last result: (i0 - 1, j)
+  float hl = 0.f;                       // horiz(i0 - 1, j)
+  int i0 = -C * j - 2 * C * s;
+  // the previous sweep at my columns i0 ... i0 + C - 1: what I read one step ago as the columns ahead ...
+  float2 Cc[C];
+#pragma unroll
+  for (int q = 0; q < C; ++q) Cc[q] = make_float2(0.f, 0.f);
+  if (s == 0) {  // ... except for the first pixels of row 0, active at step 0 (ring slots 0 ... C - 1)
+#pragma unroll
+    for (int q = 0; q < C; ++q) {
+      Cc[q] = lds64(aOld + q * strideD);
+      if (i0 + q >= w) Cc[q] = make_float2(0.f, 0.f);
+    }
+  }
+  __syncthreads();  // the loop's first fetch refills the du ring slots of step 0 just read
+  float4* gOut = a.du4 + blk + (ptrdiff_t)(i0 + C * l) * 32;  // record of pixel (i0, j): step i0 + C l of the row block
+  const int nst = (w + C - 1) / C + h - 1 + 2 * (T - 1);
+  // first and last step at which a lane of this warp is inside its row (one step early: the carried columns)
+  const int t_lo = 32 * k + 2 * s - 1, t_hi = 32 * k + 31 + 2 * s + (w + C - 1) / C;
+  for (int t = 0; t < nst; ++t) {
+    fetch();
+    const unsigned pp = resHalf - pc;  // the previous step's results
+    unsigned on = o + C * strideA;
+    on = (on == ringA) ? 0u : on;
+    float2 nv[C];
+    if (t >= t_lo && t < t_hi) {
+      float4 cA[C], cB[C];
+      float vt[C];
+      float2 U[C], Bl[C], P[C];  // (i, j-1) of this sweep; (i, j+1) and (i + C, j) of the previous sweep
+#pragma unroll
+      for (int q = 0; q < C; ++q) {
+        cA[q] = lds128(aSelf + o + q * strideA);
+        cB[q] = lds128(aSelf + offB + o + q * strideA);
+        vt[q] = lds32(aVt + om + q * strideA);  // vert(i, j-1)
+      }
+      if (C == 1) U[0] = lds64(aUp + pp);
+#pragma unroll
+      for (int q = 0; q + 1 < C; q += 2) {
+        const float4 u = lds128(aUp + pp + q * 8);
+        U[q] = make_float2(u.x, u.y);
+        U[q + 1] = make_float2(u.z, u.w);
+      }
+      if (s == 0) {
+#pragma unroll
+        for (int q = 0; q < C; ++q) {
+          P[q] = lds64(aOld + od + q * strideD);
+          Bl[q] = lds64(aBel + od + q * strideD);
+          if (i0 + C + q >= w) P[q] = make_float2(0.f, 0.f);  // the reference's zero past the last column
+        }
+      } else {
+        if (C == 1) {
+          P[0] = lds64(aOld + pp);
+          Bl[0] = lds64(aBel + pp);
+        }
+#pragma unroll
+        for (int q = 0; q + 1 < C; q += 2) {
+          const float4 p = lds128(aOld + pp + q * 8), b = lds128(aBel + pp + q * 8);
+          P[q] = make_float2(p.x, p.y);
+          P[q + 1] = make_float2(p.z, p.w);
+          Bl[q] = make_float2(b.x, b.y);
+          Bl[q + 1] = make_float2(b.z, b.w);
+        }
+      }
+      // ---- the reference's update (solver.c:122-131 / 180-190 / 237-247), both components.  First everything that
+      // does not depend on the left neighbour, for all C pixels ...
+      float s1[C], s2[C];
+#pragma unroll
+      for (int q = 0; q < C; ++q) {
+        const float2 old1 = (q < C - 1) ? Cc[q + 1 < C ? q + 1 : 0] : P[0];
+        float px = cA[q].w * old1.x, py = cA[q].w * old1.y;
+        const float ux = px + vt[q] * U[q].x, uy = py + vt[q] * U[q].y;
+        px = no_up ? px : ux;
+        py = no_up ? py : uy;
+        const float qx = px + cB[q].z * Bl[q].x, qy = py + cB[q].z * Bl[q].y;
+        px = no_dn ? px : qx;
+        py = no_dn ? py : qy;
+        s1[q] = px + cB[q].x;
+        s2[q] = py + cB[q].y;
+      }
+      // ... then the chain along the row
+      float2 left = res1;
+      float hq = hl;
+#pragma unroll
+      for (int q = 0; q < C; ++q) {
+        const float l1 = hq * left.x + s1[q], l2 = hq * left.y + s2[q];
+        const float B1 = (q == 0 && i0 == 0) ? s1[q] : l1, B2 = (q == 0 && i0 == 0) ? s2[q] : l2;
+        float2 v;
+        v.x = Cc[q].x + omega * (cA[q].x * B1 + cA[q].y * B2 - Cc[q].x);
+        v.y = Cc[q].y + omega * (cA[q].y * B1 + cA[q].z * B2 - Cc[q].y);
+        const bool act = row_ok && (unsigned)(i0 + q) < (unsigned)w;
+        v.x = act ? v.x : 0.0f;
+        v.y = act ? v.y : 0.0f;
+        nv[q] = v;
+        left = v;
+        hq = cA[q].w;
+        if (last && act) __stcg(gOut + q * 32, make_float4(v.x, v.y, 0.f, 0.f));
+      }
+      res1 = left;
+      hl = hq;
+#pragma unroll
+      for (int q = 0; q < C; ++q) Cc[q] = P[q];
+    } else {
+#pragma unroll
+      for (int q = 0; q < C; ++q) nv[q] = make_float2(0.f, 0.f);  // outside the rows: the zeros the next sweep expects
+    }
+    if (C == 1) asm volatile("st.shared.v2.f32 [%0], {%1,%2};\n" ::"r"(aOut + pc), "f"(nv[0].x), "f"(nv[0].y) : "memory");
+#pragma unroll
+    for (int q = 0; q + 1 < C; q += 2)
+      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};\n" ::"r"(aOut + pc + q * 8), "f"(nv[q].x), "f"(nv[q].y), "f"(nv[q + 1 < C ? q + 1 : q].x), "f"(nv[q + 1 < C ? q + 1 : q].y) : "memory");
+    om = o;
+    o = on;
+    od += C * strideD;
+    od = (od == ringD) ? 0u : od;
+    pc = pp;
+    gOut += 32 * C;
+    i0 += C;
+    cp_async_wait<D - 2>();  // steps <= t + 2 have landed (made visible to the other warps by the barrier)
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+}
+
 // final flow = wx + du (refine_variational.cpp:212-221)
-__global__ void __launch_bounds__(256) k_update(int w, int h, float2* __restrict__ flow, const float4* __restrict__ du4,
-                                                size_t bstride) {
+__global__ void __launch_bounds__(256) k_update(int w, int h, int skew, float2* __restrict__ flow,
+                                                const float4* __restrict__ du4, size_t bstride) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   if (i >= w || j >= h) return;
@@ -784,7 +1021,7 @@ __global__ void __launch_bounds__(256) k_update(int w, int h, float2* __restrict
   du4 = bshift_nn(du4, (size_t)blockIdx.z * bstride);
   const int o = j * w + i;
   const float2 f = flow[o];
-  const float4 d = du4[Skew(w, h).at(i, j)];
+  const float4 d = du4[Skew(w, h, skew).at(i, j)];
   flow[o] = make_float2(f.x + d.x, f.y + d.y);
 }
 
@@ -795,10 +1032,11 @@ void varref_init_device() {
   cudaFuncSetAttribute(k_sor_wavefront<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sor_smem<16>());
   cudaFuncSetAttribute(k_sor_wavefront<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sor_smem<16>());
   cudaFuncSetAttribute(k_sor_wavefront<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sor_smem<8>());
+  cudaFuncSetAttribute(k_sor_small<kSmallC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSorSmallMaxSmem);
 }
 
 void varref_sizes(int w, int h, int n_solver, size_t* n_coef4, size_t* n_du4, size_t* n_prog) {
-  const Skew sk(w, h);
+  const Skew sk(w, h, kSmallC > SK ? kSmallC : SK);  // the larger of the two layouts
   *n_coef4 = (size_t)sk.K * sk.nsp * 32;
   *n_du4 = (size_t)(sk.K + 1) * sk.nsp * 32;
   *n_prog = (size_t)n_solver * sk.K + 2;
@@ -822,22 +1060,28 @@ int launch_varref(const LevelGeom& g, const VarParams& v, const float* I0, const
   launches += 1;
 
   if (v.n_inner <= 0) return launches;
-  const Skew sk(w, h);
-  const int K = sk.K, T = v.n_solver;
+  const int K = (h + 31) / 32, T = v.n_solver;
+  // small level: one CTA per pair, one warp per (sweep, row block), kSmallC columns per step and a layout skewed by
+  // as many columns per row (measured: 2 beats 1 and 4 on every level of a 1080p pair, profiles/README.md)
+  const int small = (K <= v.sor_small && K * T <= 16 && sor_small_smem<kSmallC>(K * 32, T) <= kSorSmallMaxSmem) ? kSmallC : 0;
+  const Skew sk(w, h, small ? small : SK);
   size_t n_coef4, n_du4, n_prog;
   varref_sizes(w, h, T, &n_coef4, &n_du4, &n_prog);
   // du = dv = 0 (image_erase, refine_variational.cpp:184-185), for every pair of the batch
   cudaMemset2DAsync(b.du4, nb > 1 ? bs : sizeof(float4) * n_du4, 0, sizeof(float4) * n_du4, nb, st);
   for (int it = 0; it < v.n_inner; ++it) {
     AssembleArgs aa{w, h, v.qa, v.hg, v.hd, it == 0 ? 1 : 0, g.noc, flow, b.du4,
-                    b.stack, b.astride, b.coefA, b.coefB, b.progress, T * K, bs};
+                    b.stack, b.astride, b.coefA, b.coefB, b.progress, T * K, sk.sk, bs};
     {
       // smoothness 16 + data term 64 + sub_laplacian 32 + flow update 24 B/px
       ProfScope ps(prof, "k_assemble", g.lv, 136.0 * n);
       k_assemble<<<grid, block, 0, st>>>(aa);
     }
     SorArgs sa{w, h, T, K, v.omega, b.coefA, b.coefB, b.du4, b.progress, bs};
-    {
+    if (small) {
+      ProfScope ps(prof, "k_sor_small", g.lv, 44.0 * T * n);
+      k_sor_small<kSmallC><<<nb, K * T * 32, sor_small_smem<kSmallC>(K * 32, T), st>>>(sa, it == 0 ? 1 : 0);
+    } else {
       // each sweep reads 9 arrays and writes 2: 44 B/px
       ProfScope ps(prof, "k_sor_wavefront", g.lv, 44.0 * T * n);
       // CTAs = items busy at a time: total work (T K items of nsteps steps) over the critical path (section 4.4),
@@ -855,7 +1099,7 @@ int launch_varref(const LevelGeom& g, const VarParams& v, const float* I0, const
   }
   {
     ProfScope ps(prof, "k_update", g.lv, 8.0 * n);
-    k_update<<<grid, block, 0, st>>>(w, h, flow, b.du4, bs);
+    k_update<<<grid, block, 0, st>>>(w, h, sk.sk, flow, b.du4, bs);
   }
   return launches + 1;
 }

@@ -102,11 +102,15 @@ int dis_create_c(const dis_params* params, int channels, int max_w, int max_h, i
 int dis_destroy(dis_handle* h);
 /* Replaces the parameter set (workspace is re-planned; fails if it no longer fits). */
 int dis_set_params(dis_handle* h, const dis_params* params);
-/* Execution options; none of the first three changes results.
+/* Execution options; only DIS_OPT_ARITH changes results.
  *   DIS_OPT_SOR_GROUP  8: smaller shared-memory footprint of the SOR wavefront kernel, best pairs/s when many
  *                      handles share the GPU; 16: lowest latency for a lone pair (about 10 % at 1080p: larger groups
  *                      and one warp per (sweep, row block) item instead of persistent warps); 0 (default): persistent
  *                      warps, groups of 16 when the finest processed level has >= 2^20 pixels, else of 8.
+ *   DIS_OPT_SOR_SMALL  n: pyramid levels of at most n blocks of 32 rows run their SOR sweeps in one CTA per pair, one
+ *                      warp per (sweep, row block), two columns per barrier-separated step (k_sor_small) instead of
+ *                      the wavefront pipeline, if tv_solverit * blocks <= 16 and the rings fit in shared memory;
+ *                      0 = never; -1 (default) = 5, or 4 when DIS_OPT_SOR_GROUP is 16 (the latency setting).
  *   DIS_OPT_USE_GRAPH  1 (default): record a run into a CUDA graph and replay it; 0: launch kernel by kernel.
  * DIS_OPT_LEVEL_OUTPUT changes WHAT dis_run_u8 / dis_submit_u8 copy back, not how it is computed: 1 = the engine's
  * own output as the OFC::OFClass constructor delivers it (level lv_l, (w_pad/2^lv_l) x (h_pad/2^lv_l) x 2 floats,
@@ -120,7 +124,9 @@ int dis_set_params(dis_handle* h, const dis_params* params);
  * operating points with maxiter <= 32, which is enforced: a run with more iterations fails with
  * DIS_ERR_UNSUPPORTED (rounding differences grow with the iteration count, 0.25 px at 128).  It is never part of a
  * parity claim; bench.py reports it as a separate line (--arith fast). */
-typedef enum dis_option { DIS_OPT_SOR_GROUP = 1, DIS_OPT_USE_GRAPH = 2, DIS_OPT_LEVEL_OUTPUT = 3, DIS_OPT_ARITH = 4 } dis_option;
+typedef enum dis_option {
+  DIS_OPT_SOR_GROUP = 1, DIS_OPT_USE_GRAPH = 2, DIS_OPT_LEVEL_OUTPUT = 3, DIS_OPT_ARITH = 4, DIS_OPT_SOR_SMALL = 5
+} dis_option;
 int dis_set_option(dis_handle* h, int option, int value);
 /* Last error text of this handle (or of dis_create when h is NULL). Never NULL. */
 const char* dis_last_error(const dis_handle* h);

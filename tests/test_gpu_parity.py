@@ -249,7 +249,7 @@ def test_engine_reuse_across_sizes_and_params():
 
 
 def test_execution_options_do_not_change_results():
-    """DIS_OPT_SOR_GROUP (8 | 16) and DIS_OPT_USE_GRAPH only change how the work is scheduled."""
+    """DIS_OPT_SOR_GROUP (8 | 16), DIS_OPT_SOR_SMALL and DIS_OPT_USE_GRAPH only change how the work is scheduled."""
     a, b, _ = synth_pair(500, 300, seed=21)
     p = params(3, 512, lv_f=3, lv_l=0)
     ref = port.run_u8(a, b, p.to_dict())
@@ -262,6 +262,13 @@ def test_execution_options_do_not_change_results():
                 assert bits_differ(e.run_u8(a, b), ref) == 0, (grp, graph)  # replay
         with pytest.raises(F.DisError):
             e.set_option(api.OPT_SOR_GROUP, 12)
+        # OPT_SOR_SMALL: which levels take the one-CTA SOR (never, the default, every level it can hold: 320 rows -> 288 max)
+        e.set_option(api.OPT_SOR_GROUP, 0)
+        for small in (0, 2, 9, -1):
+            e.set_option(api.OPT_SOR_SMALL, small)
+            assert bits_differ(e.run_u8(a, b), ref) == 0, small
+        with pytest.raises(F.DisError):
+            e.set_option(api.OPT_SOR_SMALL, 10)
         # OPT_LEVEL_OUTPUT: the OFClass-style output; the caller's resize + crop (here: the oracle's) gives the same flow
         e.set_option(api.OPT_LEVEL_OUTPUT, 1)
         lvl = e.run_u8(a, b)
