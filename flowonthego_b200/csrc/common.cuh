@@ -5,6 +5,7 @@
 // no flush-to-zero, so that `a*b + c` rounds twice exactly like the reference's -msse4 build.
 #pragma once
 #include <cuda_runtime.h>
+#include <utility>
 #include <stdint.h>
 
 struct dis_handle;
@@ -57,6 +58,28 @@ struct VarParams {  // kroeger/refine_variational.cpp:28-42
   int sor_full;   // 1: one CTA per (sweep, row block) item -- lowest latency for a lone pair; 0: only as many CTAs as
                   // items are busy at a time, each warp taking ticket after ticket (best pairs/s)
 };
+
+// Programmatic dependent launch: a kernel launched through launch_pdl may be scheduled while its predecessor in the
+// stream (or captured graph) is still draining; it must call pdl_wait() before it touches anything the predecessor
+// wrote -- here: as its first statement, so only the launch latency and the block scheduling overlap.  Every kernel of
+// the chain calls pdl_wait(), which makes completion transitive (a kernel cannot finish before its predecessor has).
+// (No early griddepcontrol.launch_dependents: measured, it makes dependents resident that only wait -- lone pair 1.60
+// -> 1.67 ms, -2 % pairs/s, -27 % through the video front end.)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
 
 // Optional per-kernel profiling hook (CUDA events around every launch; used by bench.py's roofline
 // leg through dis_profile_kernels, never on the timed path).

@@ -41,6 +41,7 @@ __device__ __forceinline__ float patch_absw(const float* pw, int P, int noc, int
 // weights (:310-315) and the level-wide maximum anchor displacement.
 __global__ void __launch_bounds__(256) k_bw_anchors(const LevelGeom g, const OptParams o, const float2* __restrict__ pflow0,
                                                     int2* __restrict__ anchor0, float4* __restrict__ wbil0, int* __restrict__ maxdisp0) {
+  pdl_wait();
   const int ip = blockIdx.x * blockDim.x + threadIdx.x;
   if (ip >= g.nop) return;
   const size_t boff = (size_t)blockIdx.y * g.bstride;  // blockIdx.y = pair of a batched handle
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(256) k_bw_anchors(const LevelGeom g, const Opt
 
 template <bool FB>
 __global__ void __launch_bounds__(256, 2) k_densify(const DensifyArgs a) {
+  pdl_wait();
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= a.g.w || y >= a.g.h) return;
@@ -188,10 +190,10 @@ void launch_densify(const DensifyArgs& a, cudaStream_t st) {
   dim3 grid((a.g.w + 31) / 32, (a.g.h + 7) / 8, a.g.nb);
   if (a.pflow_bw != nullptr) {
     cudaMemset2DAsync(a.maxdisp, a.g.bstride ? a.g.bstride : sizeof(int), 0, sizeof(int), a.g.nb, st);  // one counter per pair
-    k_bw_anchors<<<dim3((a.g.nop + 255) / 256, a.g.nb), 256, 0, st>>>(a.g, a.o, a.pflow_bw, a.anchor, a.wbil, a.maxdisp);
-    k_densify<true><<<grid, block, 0, st>>>(a);
+    launch_pdl(k_bw_anchors, dim3((a.g.nop + 255) / 256, a.g.nb), dim3(256), 0, st, a.g, a.o, a.pflow_bw, a.anchor, a.wbil, a.maxdisp);
+    launch_pdl(k_densify<true>, grid, block, 0, st, a);
   } else {
-    k_densify<false><<<grid, block, 0, st>>>(a);
+    launch_pdl(k_densify<false>, grid, block, 0, st, a);
   }
 }
 

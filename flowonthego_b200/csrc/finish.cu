@@ -25,6 +25,7 @@ __device__ __forceinline__ void export_level(const float2* __restrict__ fl, int 
 __global__ void __launch_bounds__(256) k_finish(const float2* __restrict__ fl, int wl, int hl, int lv_l,
                                                 int left, int top, int w_org, int h_org,
                                                 const Mailbox* __restrict__ mb, size_t bstride) {
+  pdl_wait();
   fl = bshift_nn(fl, (size_t)blockIdx.z * bstride);  // blockIdx.z = pair of a batched handle
   mb = bshift_nn(mb, (size_t)blockIdx.z * bstride);
   float2* __restrict__ out = mb->out;
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(256) k_finish(const float2* __restrict__ fl, i
 // touch the border clamps or the crop edge fall back to the per-pixel form.
 __global__ void __launch_bounds__(256) k_finish_x4(const float2* __restrict__ fl, int wl, int hl, int left, int top,
                                                    int w_org, int h_org, const Mailbox* __restrict__ mb, size_t bstride) {
+  pdl_wait();
   fl = bshift_nn(fl, (size_t)blockIdx.z * bstride);  // blockIdx.z = pair of a batched handle
   mb = bshift_nn(mb, (size_t)blockIdx.z * bstride);
   float2* __restrict__ out = mb->out;
@@ -170,11 +172,11 @@ void launch_finish(const float2* flow_l, int wl, int hl, int lv_l, int left, int
                    const Mailbox* mb, int nb, size_t bstride, cudaStream_t st) {
   if (lv_l == 2 && (left & 3) == 0 && (top & 3) == 0) {
     dim3 block(32, 8), grid((w_org + 127) / 128, (h_org + 31) / 32, nb);
-    k_finish_x4<<<grid, block, 0, st>>>(flow_l, wl, hl, left, top, w_org, h_org, mb, bstride);
+    launch_pdl(k_finish_x4, grid, block, 0, st, flow_l, wl, hl, left, top, w_org, h_org, mb, bstride);
     return;
   }
   dim3 block(32, 8), grid((w_org + 127) / 128, (h_org + 7) / 8, nb);
-  k_finish<<<grid, block, 0, st>>>(flow_l, wl, hl, lv_l, left, top, w_org, h_org, mb, bstride);
+  launch_pdl(k_finish, grid, block, 0, st, flow_l, wl, hl, lv_l, left, top, w_org, h_org, mb, bstride);
 }
 
 }  // namespace dis

@@ -66,6 +66,7 @@ struct Win {
 // re-read per iteration instead of being held in registers.
 template <int P, bool L2, int NC>
 __global__ void __launch_bounds__(kPsThreads, (P == 12 && NC == 1) ? 512 / kPsThreads : 1) k_patch_search(const PatchSearchArgs a) {
+  pdl_wait();
   // batched handles: blockIdx.y = pair, all buffers of that pair sit a.g.bstride bytes further (common.cuh)
   const size_t boff = (size_t)blockIdx.y * a.g.bstride;
   const float* __restrict__ pI0 = bshift_nn(a.I0, boff);
@@ -361,13 +362,13 @@ int launch_p(const PatchSearchArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)(threads / 8) * Win<P>::SIZE * sizeof(float);
   if (a.o.noc == 3) {
     if (a.o.costfct == 0)
-      k_patch_search<P, true, 3><<<dim3(blocks, a.g.nb), threads, 0, st>>>(a);
+      launch_pdl(k_patch_search<P, true, 3>, dim3(blocks, a.g.nb), dim3(threads), 0, st, a);
     else
-      k_patch_search<P, false, 3><<<dim3(blocks, a.g.nb), threads, 0, st>>>(a);
+      launch_pdl(k_patch_search<P, false, 3>, dim3(blocks, a.g.nb), dim3(threads), 0, st, a);
   } else if (a.o.costfct == 0)
-    k_patch_search<P, true, 1><<<dim3(blocks, a.g.nb), threads, smem, st>>>(a);
+    launch_pdl(k_patch_search<P, true, 1>, dim3(blocks, a.g.nb), dim3(threads), smem, st, a);
   else
-    k_patch_search<P, false, 1><<<dim3(blocks, a.g.nb), threads, smem, st>>>(a);
+    launch_pdl(k_patch_search<P, false, 1>, dim3(blocks, a.g.nb), dim3(threads), smem, st, a);
   return 0;
 }
 

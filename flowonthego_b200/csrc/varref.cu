@@ -86,6 +86,7 @@ struct FrontArgs {
 };
 
 __global__ void __launch_bounds__(256) k_front(const FrontArgs a) {
+  pdl_wait();
   enum { S_IZ = 1, S_IX = 2, S_IY = 3, S_IXX = 4, S_IXY = 5, S_IYY = 6, S_IXZ = 7, S_IYZ = 8, S_MASK = 9 };
   __shared__ float avg_s[FTY + 8][FTX + 8], iz_s[FTY + 8][FTX + 8];
   __shared__ float ix_s[FTY + 4][FTX + 4], iy_s[FTY + 4][FTX + 4];
@@ -231,6 +232,7 @@ constexpr int ATX = 32, ATY = 8;
 // 8 blocks per SM (32 registers, a few spills): the kernel waits on global loads, so resident warps beat registers
 // (+3 % pairs/s against the compiler's own choice of 48 registers, A/B in one session)
 __global__ void __launch_bounds__(ATX* ATY, 8) k_assemble(const AssembleArgs a_in) {
+  pdl_wait();
   AssembleArgs a = a_in;
   {
     const size_t boff = (size_t)blockIdx.z * a.bstride;
@@ -491,6 +493,7 @@ __device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
 
 template <int kG, bool kPersistent>
 __global__ void __launch_bounds__(32, kG == 8 ? 16 : 8) k_sor_wavefront(const SorArgs a_in) {
+  pdl_wait();
   constexpr int kCH = kG, kRD = 2 * kG;
   SorArgs a = a_in;
   {
@@ -820,6 +823,7 @@ inline size_t sor_small_smem(int rows, int T) {
 
 template <int C>
 __global__ void __launch_bounds__(512) k_sor_small(const SorArgs a_in, const int first) {
+  pdl_wait();
   constexpr int D = SorSmallDist<C>::value;
   SorArgs a = a_in;
   {
@@ -1014,6 +1018,7 @@ __global__ void __launch_bounds__(512) k_sor_small(const SorArgs a_in, const int
 // final flow = wx + du (refine_variational.cpp:212-221)
 __global__ void __launch_bounds__(256) k_update(int w, int h, int skew, float2* __restrict__ flow,
                                                 const float4* __restrict__ du4, size_t bstride) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   if (i >= w || j >= h) return;
@@ -1055,7 +1060,7 @@ int launch_varref(const LevelGeom& g, const VarParams& v, const float* I0, const
   {
     ProfScope ps(prof, "k_front", g.lv, 68.0 * n);
     FrontArgs fa{w, h, g.pad, g.pitch, g.noc, I0, I1, flow, b.stack, b.astride, bs};
-    k_front<<<dim3((w + FTX - 1) / FTX, (h + FTY - 1) / FTY, nb), dim3(32, 8), 0, st>>>(fa);
+    launch_pdl(k_front, dim3((w + FTX - 1) / FTX, (h + FTY - 1) / FTY, nb), dim3(32, 8), 0, st, fa);
   }
   launches += 1;
 
@@ -1075,12 +1080,12 @@ int launch_varref(const LevelGeom& g, const VarParams& v, const float* I0, const
     {
       // smoothness 16 + data term 64 + sub_laplacian 32 + flow update 24 B/px
       ProfScope ps(prof, "k_assemble", g.lv, 136.0 * n);
-      k_assemble<<<grid, block, 0, st>>>(aa);
+      launch_pdl(k_assemble, grid, block, 0, st, aa);
     }
     SorArgs sa{w, h, T, K, v.omega, b.coefA, b.coefB, b.du4, b.progress, bs};
     if (small) {
       ProfScope ps(prof, "k_sor_small", g.lv, 44.0 * T * n);
-      k_sor_small<kSmallC><<<nb, K * T * 32, sor_small_smem<kSmallC>(K * 32, T), st>>>(sa, it == 0 ? 1 : 0);
+      launch_pdl(k_sor_small<kSmallC>, dim3(nb), dim3(K * T * 32), sor_small_smem<kSmallC>(K * 32, T), st, sa, it == 0 ? 1 : 0);
     } else {
       // each sweep reads 9 arrays and writes 2: 44 B/px
       ProfScope ps(prof, "k_sor_wavefront", g.lv, 44.0 * T * n);
@@ -1089,17 +1094,17 @@ int launch_varref(const LevelGeom& g, const VarParams& v, const float* I0, const
       const int lag = 80, path = sk.nsteps + (K - 1 + 2 * (T - 1)) * lag;
       const int ctas = v.sor_full ? T * K : std::min(T * K, (int)(((long long)T * K * sk.nsteps + path - 1) / path) + 3);
       if (v.sor_full)
-        k_sor_wavefront<16, false><<<dim3(ctas, nb), 32, sor_smem<16>(), st>>>(sa);
+        launch_pdl(k_sor_wavefront<16, false>, dim3(ctas, nb), dim3(32), sor_smem<16>(), st, sa);
       else if (v.sor_group == 16)
-        k_sor_wavefront<16, true><<<dim3(ctas, nb), 32, sor_smem<16>(), st>>>(sa);
+        launch_pdl(k_sor_wavefront<16, true>, dim3(ctas, nb), dim3(32), sor_smem<16>(), st, sa);
       else
-        k_sor_wavefront<8, true><<<dim3(ctas, nb), 32, sor_smem<8>(), st>>>(sa);
+        launch_pdl(k_sor_wavefront<8, true>, dim3(ctas, nb), dim3(32), sor_smem<8>(), st, sa);
     }
     launches += 2;
   }
   {
     ProfScope ps(prof, "k_update", g.lv, 8.0 * n);
-    k_update<<<grid, block, 0, st>>>(w, h, sk.sk, flow, b.du4, bs);
+    launch_pdl(k_update, grid, block, 0, st, w, h, sk.sk, flow, (const float4*)b.du4, bs);
   }
   return launches + 1;
 }
