@@ -852,30 +852,33 @@ __global__ void __launch_bounds__(512) k_sor_small(const SorArgs a_in, const int
   }
   __syncthreads();
   // Fetch duty: per step the C wavefront steps u .. u + C - 1 of the layout (columns u - C j ... of row j) = steps
-  // u - 32 C k of a row block, 512 contiguous bytes per array, row block and wavefront step.  The three arrays are
-  // shared out over the sweeps' warps of a row block: array q (coefA, coefB, du records) goes to sweep q mod T.
-  const bool f_a = (0 % T) == s, f_b = (1 % T) == s, f_d = (2 % T) == s && !first;
-  const float4* fA = a.coefA + blk - (ptrdiff_t)(32 * C * k) * 32;
-  const float4* fB = a.coefB + blk - (ptrdiff_t)(32 * C * k) * 32;
-  const float4* fD = a.du4 + blk - (ptrdiff_t)(32 * C * k) * 32;
+  // u - 32 C k of a row block, 512 contiguous bytes per array, row block and wavefront step.  Warp (s, k) fetches
+  // array s of row block k: 0 coefA, 1 coefB, 2 the du records (not in the first iteration); with fewer than three
+  // sweeps the block has fetch-only warps s = T ... 2.
+  const int duty = (s > 2 || (s == 2 && first)) ? -1 : s;
+  const unsigned char* fsrc = reinterpret_cast<const unsigned char*>((duty == 0 ? a.coefA : duty == 1 ? a.coefB : a.du4) + blk) -
+                              (ptrdiff_t)(32 * C * k) * 512;
+  const unsigned fstride = duty == 2 ? strideD : strideA, fring = duty == 2 ? ringD : ringA;
+  const unsigned fdst = sb + (duty == 1 ? offB : duty == 2 ? offD : 0u) + j * (duty == 2 ? 8 : 16);
   int fsp = -32 * C * k;
-  unsigned fo = 0, fod = 0;
+  unsigned fo = 0;
   auto fetch = [&]() {
+    if (duty == 2) {
 #pragma unroll
-    for (int q = 0; q < C; ++q)
-      if ((unsigned)(fsp + q) < (unsigned)nsteps) {
-        const unsigned d = sb + fo + q * strideA + j * 16;
-        if (f_a) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(fA + q * 32) : "memory");
-        if (f_b) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d + offB), "l"(fB + q * 32) : "memory");
-        if (f_d) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sb + offD + fod + q * strideD + j * 8), "l"(fD + q * 32) : "memory");
-      }
+      for (int q = 0; q < C; ++q)
+        if ((unsigned)(fsp + q) < (unsigned)nsteps)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(fdst + fo + q * fstride), "l"(fsrc + q * 512) : "memory");
+    } else if (duty >= 0) {
+#pragma unroll
+      for (int q = 0; q < C; ++q)
+        if ((unsigned)(fsp + q) < (unsigned)nsteps)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(fdst + fo + q * fstride), "l"(fsrc + q * 512) : "memory");
+    }
     cp_async_commit();
-    fA += 32 * C; fB += 32 * C; fD += 32 * C;
+    fsrc += 512 * C;
     fsp += C;
-    fo += C * strideA;
-    fo = (fo == ringA) ? 0u : fo;
-    fod += C * strideD;
-    fod = (fod == ringD) ? 0u : fod;
+    fo += C * fstride;
+    fo = (fo == fring) ? 0u : fo;
   };
   for (int u = 0; u < D; ++u) fetch();
   cp_async_wait<D - 2>();  // steps 0 and 1 have landed
@@ -918,7 +921,7 @@ __global__ void __launch_bounds__(512) k_sor_small(const SorArgs a_in, const int
     unsigned on = o + C * strideA;
     on = (on == ringA) ? 0u : on;
     float2 nv[C];
-    if (t >= t_lo && t < t_hi) {
+    if (s < T && t >= t_lo && t < t_hi) {
       float4 cA[C], cB[C];
       float vt[C];
       float2 U[C], Bl[C], P[C];  // (i, j-1) of this sweep; (i, j+1) and (i + C, j) of the previous sweep
@@ -998,9 +1001,9 @@ __global__ void __launch_bounds__(512) k_sor_small(const SorArgs a_in, const int
 #pragma unroll
       for (int q = 0; q < C; ++q) nv[q] = make_float2(0.f, 0.f);  // outside the rows: the zeros the next sweep expects
     }
-    if (C == 1) asm volatile("st.shared.v2.f32 [%0], {%1,%2};\n" ::"r"(aOut + pc), "f"(nv[0].x), "f"(nv[0].y) : "memory");
+    if (C == 1 && s < T) asm volatile("st.shared.v2.f32 [%0], {%1,%2};\n" ::"r"(aOut + pc), "f"(nv[0].x), "f"(nv[0].y) : "memory");
 #pragma unroll
-    for (int q = 0; q + 1 < C; q += 2)
+    for (int q = 0; q + 1 < C && s < T; q += 2)
       asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};\n" ::"r"(aOut + pc + q * 8), "f"(nv[q].x), "f"(nv[q].y), "f"(nv[q + 1 < C ? q + 1 : q].x), "f"(nv[q + 1 < C ? q + 1 : q].y) : "memory");
     om = o;
     o = on;
@@ -1068,7 +1071,7 @@ int launch_varref(const LevelGeom& g, const VarParams& v, const float* I0, const
   const int K = (h + 31) / 32, T = v.n_solver;
   // small level: one CTA per pair, one warp per (sweep, row block), kSmallC columns per step and a layout skewed by
   // as many columns per row (measured: 2 beats 1 and 4 on every level of a 1080p pair, profiles/README.md)
-  const int small = (K <= v.sor_small && K * T <= 16 && sor_small_smem<kSmallC>(K * 32, T) <= kSorSmallMaxSmem) ? kSmallC : 0;
+  const int small = (K <= v.sor_small && K * std::max(T, 3) <= 16 && sor_small_smem<kSmallC>(K * 32, T) <= kSorSmallMaxSmem) ? kSmallC : 0;
   const Skew sk(w, h, small ? small : SK);
   size_t n_coef4, n_du4, n_prog;
   varref_sizes(w, h, T, &n_coef4, &n_du4, &n_prog);
@@ -1085,7 +1088,8 @@ int launch_varref(const LevelGeom& g, const VarParams& v, const float* I0, const
     SorArgs sa{w, h, T, K, v.omega, b.coefA, b.coefB, b.du4, b.progress, bs};
     if (small) {
       ProfScope ps(prof, "k_sor_small", g.lv, 44.0 * T * n);
-      launch_pdl(k_sor_small<kSmallC>, dim3(nb), dim3(K * T * 32), sor_small_smem<kSmallC>(K * 32, T), st, sa, it == 0 ? 1 : 0);
+      launch_pdl(k_sor_small<kSmallC>, dim3(nb), dim3(K * std::max(T, 3) * 32), sor_small_smem<kSmallC>(K * 32, T), st, sa,
+                 it == 0 ? 1 : 0);
     } else {
       // each sweep reads 9 arrays and writes 2: 44 B/px
       ProfScope ps(prof, "k_sor_wavefront", g.lv, 44.0 * T * n);

@@ -28,3 +28,12 @@ for name, m in sorted(agg.items(), key=lambda kv: -kv[1].get("gpu__time_duration
     print("%-22s %4d %10.4f %10.2f %10.2f %12.2f" % (name, cnt[name], t, rd / 1e6, wr / 1e6, ins / 1e6))
     for k, v in (("t", t), ("rd", rd), ("wr", wr), ("ins", ins)): tot[k] += v
 print("%-22s %4d %10.4f %10.2f %10.2f %12.2f" % ("TOTAL", sum(cnt.values()), tot["t"], tot["rd"] / 1e6, tot["wr"] / 1e6, tot["ins"] / 1e6))
+if len(sys.argv) > 2:  # json for bench.py's roofline.traffic: per kernel name of one pair
+    import json
+    per = {}
+    for name, m in sorted(agg.items(), key=lambda kv: -kv[1].get("gpu__time_duration.sum", 0)):
+        per[name] = {"launches": cnt[name], "time_ms": round(m.get("gpu__time_duration.sum", 0), 4),
+                     "dram_read_MB": round(m.get("dram__bytes_read.sum", 0) / 1e6, 2),
+                     "dram_write_MB": round(m.get("dram__bytes_write.sum", 0) / 1e6, 2),
+                     "warp_inst_M": round(m.get("smsp__inst_executed.sum", 0) / 1e6, 2)}
+    json.dump({"what": sys.argv[3] if len(sys.argv) > 3 else "", "per_pair": per}, open(sys.argv[2], "w"), indent=1)
