@@ -296,6 +296,22 @@ def test_many_sor_sweeps_and_inner_iterations():
         F.Engine(params(2, 1024, tv_solverit=300), 200, 140)
 
 
+def test_sor_small_kernel_shapes():
+    """k_sor_small (one CTA per pair, two columns per step): 1 ... 5 sweeps (fewer than three sweeps add fetch-only
+    warps), odd widths (the last step of a row holds one pixel), levels narrower than a step pair, 1 ... 5 row blocks,
+    several inner iterations (sweep 0 reads the previous launch's records), colour."""
+    for (w, h, ch, kw) in ((61, 45, 1, dict(tv_solverit=1, tv_innerit=2)), (130, 97, 1, dict(tv_solverit=4)),
+                           (35, 33, 1, dict(tv_solverit=3, tv_innerit=3, tv_sor=1.9)), (258, 150, 1, dict(tv_solverit=3)),
+                           (22, 140, 1, dict(tv_solverit=2)), (99, 70, 3, dict(tv_solverit=5, tv_innerit=2))):
+        a, b, _ = (synth_pair if ch == 1 else synth_pair_bgr)(w, h, seed=w + h)
+        p = params(2, 1024, lv_f=1, lv_l=0, maxiter=6, miniter=6, **kw)
+        ref = port.run_u8(a, b, p.to_dict())
+        with F.Engine(p, w, h, channels=ch) as e:
+            assert bits_differ(e.run_u8(a, b), ref) == 0, (w, h, kw)
+            e.set_option(api.OPT_SOR_SMALL, 0)  # the wavefront pipeline on the same levels
+            assert bits_differ(e.run_u8(a, b), ref) == 0, (w, h, kw, "wavefront")
+
+
 @pytest.mark.parametrize("channels,usefbcon,batch", [(1, 0, 4), (1, 1, 3), (3, 0, 2)])
 def test_batched_handle(channels, usefbcon, batch):
     """dis_create_batch: every launch serves `batch` pairs; each pair equals a separate run, also with fewer pairs
