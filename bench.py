@@ -12,7 +12,8 @@ Workloads:
                  p12 ov0.75 lv7->0 16it + variational refinement;  c4b: the same with 128 iterations
 One step = one pass of the whole hot path (pyramid -> inverse search -> densify -> refine -> upsample) over
 `batch` consecutive frame pairs per GPU.  Independent pairs shard across ranks with no data-path collective
-(weak scaling: the per-GPU batch is fixed).
+(weak scaling: the per-GPU batch is fixed; `--total-pairs P` fixes the job instead -- P / N pairs per GPU and step,
+"scaling": "strong"; P = 1024 is the C5 stream of BASELINE.md).
 
   value : pairs/s with the frames already resident in HBM; full-resolution flow left in HBM; with N > 1 the
           engine's level flows of every step are gathered on rank 0 over NCCL (overlapped with the next step)
@@ -244,7 +245,7 @@ class Bench:
         self.local_rank = local_rank
         self.dist = None
         self.W, self.H = cfg["w"], cfg["h"]
-        self.B = args.batch or cfg["batch"]
+        self.B = (args.total_pairs // self.world if args.total_pairs else 0) or args.batch or cfg["batch"]
         self.S = max(1, min(args.streams or cfg["streams"], self.B))
         self.nb = max(1, min(args.pairs_per_launch if args.pairs_per_launch is not None else cfg["nb"], 8, self.B))
         self.Sb = max(1, args.batch_handles or cfg["bh"] or 1)
@@ -580,6 +581,8 @@ def main():
     ap.add_argument("--arith", default="exact", choices=["exact", "fast"],
                     help="fast = DIS_OPT_ARITH tolerance mode (FMA contraction; NOT the parity claim), see DESIGN.md")
     ap.add_argument("--batch", type=int, default=0, help="frame pairs per step per GPU (default: per config)")
+    ap.add_argument("--total-pairs", type=int, default=0,
+                    help="strong scaling: frame pairs per step over ALL GPUs (1024 = the C5 stream); default: weak scaling")
     ap.add_argument("--streams", type=int, default=0, help="engine instances (CUDA streams) per GPU for the host-buffer arms")
     ap.add_argument("--pairs-per-launch", type=int, default=None,
                     help="batched handles for the device-resident arm (dis_create_batch); 1 = one pair per launch")
@@ -598,7 +601,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     N, K, Wm = args.gpus, args.steps, max(args.warmup, 0)
     cfg = dict(CONFIGS[args.config], key=args.config)
-    B = args.batch or cfg["batch"]
+    B = (args.total_pairs // world if args.total_pairs else 0) or args.batch or cfg["batch"]
+    scaling = "strong" if args.total_pairs else "weak"
     pd = params_dict(cfg["argv"])
     S = max(1, min(args.streams or cfg["streams"], B))
     nb = max(1, min(args.pairs_per_launch if args.pairs_per_launch is not None else cfg["nb"], 8, B))
@@ -634,7 +638,7 @@ def main():
         v = cb["value"]
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": N,
                           "steps": Kr, "warmup": Wr, "ms_per_step": 1e3 * sum(walls) / len(walls),
-                          "ms_per_pair": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "ms_per_pair": 1e3 / v, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
                           "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": cb,
                           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}),
               file=json_out, flush=True)
@@ -709,7 +713,7 @@ def main():
     if rank == 0:
         calls = dev_res["calls_per_step"]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": K, "warmup": Wm,
-                "ms_per_step": ms / K, "ms_per_pair": ms / K / B, "higher_is_better": True, "scaling": "weak",
+                "ms_per_step": ms / K, "ms_per_pair": ms / K / B, "higher_is_better": True, "scaling": scaling,
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "e2e": e2e, "gpu_launches": int(dev_res["launches_per_call"]) * calls * K,
                 "launches_per_pair": dev_res["launches_per_call"] / nb, "pairs_per_launch": nb,
