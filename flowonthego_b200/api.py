@@ -229,7 +229,7 @@ class Engine:
         _check(lib().dis_set_params(self._h, ctypes.byref(self.params)), self._h)
 
     def set_option(self, option, value):
-        """OPT_SOR_GROUP (8 | 16), OPT_SOR_SMALL (0 ... 9), OPT_USE_GRAPH (0 | 1), OPT_LEVEL_OUTPUT: results never change.
+        """OPT_SOR_GROUP (8 | 16), OPT_SOR_SMALL (-1 auto | 0 ... 9 row blocks), OPT_USE_GRAPH (0 | 1), OPT_LEVEL_OUTPUT: results never change.
         OPT_ARITH (0 exact | 1 tolerance mode, FMA contraction; maxiter <= 32 only) does change them."""
         _check(lib().dis_set_option(self._h, int(option), int(value)), self._h)
         if int(option) == OPT_LEVEL_OUTPUT:

@@ -109,7 +109,7 @@ int dis_set_params(dis_handle* h, const dis_params* params);
  *                      warps, groups of 16 when the finest processed level has >= 2^20 pixels, else of 8.
  *   DIS_OPT_SOR_SMALL  n: pyramid levels of at most n blocks of 32 rows run their SOR sweeps in one CTA per pair, one
  *                      warp per (sweep, row block), two columns per barrier-separated step (k_sor_small) instead of
- *                      the wavefront pipeline, if tv_solverit * blocks <= 16 and the rings fit in shared memory;
+ *                      the wavefront pipeline, if max(tv_solverit, 3) * blocks <= 16 and the rings fit in shared memory;
  *                      0 = never; -1 (default) = 5, or 4 when DIS_OPT_SOR_GROUP is 16 (the latency setting).
  *   DIS_OPT_USE_GRAPH  1 (default): record a run into a CUDA graph and replay it; 0: launch kernel by kernel.
  * DIS_OPT_LEVEL_OUTPUT changes WHAT dis_run_u8 / dis_submit_u8 copy back, not how it is computed: 1 = the engine's
