@@ -248,6 +248,7 @@ class Bench:
         self.B = (args.total_pairs // self.world if args.total_pairs else 0) or args.batch or cfg["batch"]
         self.S = max(1, min(args.streams or cfg["streams"], self.B))
         self.nb = max(1, min(args.pairs_per_launch if args.pairs_per_launch is not None else cfg["nb"], 8, self.B))
+        self.nb_e2e = max(1, min(args.e2e_pairs_per_launch if args.e2e_pairs_per_launch is not None else self.nb, 8))
         self.Sb = max(1, args.batch_handles or cfg["bh"] or 1)
         self.p = F.Params.from_argv(cfg["argv"].split())
         self.arith = args.arith
@@ -402,12 +403,14 @@ class Bench:
         B, W, H, S = self.B, self.W, self.H, self.S
         L = F.lib()
         vid = ctypes.c_void_p()
-        rc = L.dis_video_create(ctypes.byref(self.p), 1, W, H, self.local_rank, S, ctypes.byref(vid))
+        nbv = self.nb_e2e if S % max(self.nb_e2e, 1) == 0 else 1  # pairs per launch of the video front end
+        rc = L.dis_video_create_batched(ctypes.byref(self.p), 1, W, H, self.local_rank, S, nbv, ctypes.byref(vid))
         if rc != 0:
             raise RuntimeError(L.dis_last_error(None).decode())
+        nH = L.dis_video_handles(vid)
         if self.arith == "fast":
             from flowonthego_b200 import api
-            for k in range(S):
+            for k in range(nH):
                 L.dis_set_option(L.dis_video_handle(vid, k), api.OPT_ARITH, 1)
         fw, fh = ctypes.c_int(), ctypes.c_int()
         nfl = L.dis_video_flow_size(vid, ctypes.byref(fw), ctypes.byref(fh))
@@ -417,7 +420,7 @@ class Bench:
         fp = ctypes.POINTER(ctypes.c_float)
         outp = [x.ctypes.data_as(fp) for x in h_lvl]
         inp = [h_frames[i].ctypes.data for i in range(B + 1)]
-        streams = [torch.cuda.ExternalStream(L.dis_stream(L.dis_video_handle(vid, k)), device=self.dev) for k in range(S)]
+        streams = [torch.cuda.ExternalStream(L.dis_stream(L.dis_video_handle(vid, k)), device=self.dev) for k in range(nH)]
         push, pop, pending = L.dis_video_push, L.dis_video_pop, L.dis_video_pending
         npush = [0]
 
@@ -441,7 +444,8 @@ class Bench:
         L.dis_video_destroy(vid)
         return dict(value=self.world * B * K / (ms / 1e3), unit=UNIT, h2d_bytes_per_step=W * H * B,
                     d2h_bytes_per_step=int(nfl) * 4 * B, steps=K, ms_per_step=ms / K, pairs_in_flight=S,
-                    api="dis_video_push/dis_video_pop (include/dis_c.h): pinned host u8 frames in, each uploaded once; "
+                    pairs_per_launch=nbv,
+                    api="dis_video_create_batched/dis_video_push/dis_video_pop (include/dis_c.h): pinned host u8 frames in, each uploaded once; "
                         "per pair the engine's own output -- OFC::OFClass outflow, level-%d flow %dx%d -- copied to pinned "
                         "host memory (DIS_VIDEO_OUT_LEVEL, the stream default)" % (self.p.lv_l, fw.value, fh.value),
                     mean_abs_level_flow=float(np.abs(h_lvl[0]).mean()))
@@ -597,6 +601,8 @@ def main():
     ap.add_argument("--pairs-per-launch", type=int, default=None,
                     help="batched handles for the device-resident arm (dis_create_batch); 1 = one pair per launch")
     ap.add_argument("--batch-handles", type=int, default=0, help="number of batched handles per GPU")
+    ap.add_argument("--e2e-pairs-per-launch", type=int, default=None,
+                    help="pairs per launch of the video front end in the e2e arm (default: as --pairs-per-launch; 1 = dis_video_create)")
     ap.add_argument("--nccl-channels", type=int, default=0, help="NCCL_MAX_NCHANNELS for the result gather (default: by N)")
     ap.add_argument("--no-gather", action="store_true", help="N > 1: leave the level flows on their GPUs (diagnostic)")
     ap.add_argument("--no-extra", action="store_true", help="skip the side measurements (4K, full-flow e2e, latency)")

@@ -126,6 +126,8 @@ def lib():
         L.dis_read_image_gray.argtypes = [ctypes.c_char_p, vp, ctypes.c_size_t, ctypes.POINTER(ip), ctypes.POINTER(ip)]
         L.dis_read_image_bgr.argtypes = L.dis_read_image_gray.argtypes
         L.dis_video_create.argtypes = [pp, ip, ip, ip, ip, ip, ctypes.POINTER(vp)]
+        L.dis_video_create_batched.argtypes = [pp, ip, ip, ip, ip, ip, ip, ctypes.POINTER(vp)]
+        L.dis_video_handles.argtypes = [vp]
         L.dis_video_destroy.argtypes = [vp]
         L.dis_video_destroy.restype = None
         L.dis_video_push.argtypes = [vp, vp, ip, fp]
@@ -377,12 +379,13 @@ class FlowStream:
     Engine.level_flow() of that pair bit for bit; output="full": the full-resolution (h, w, 2) field, equal to
     Engine.run_u8 on that pair bit for bit."""
 
-    def __init__(self, params, w, h, depth=8, device=0, channels=1, output="level", reuse=None):
+    def __init__(self, params, w, h, depth=8, device=0, channels=1, output="level", reuse=None, pairs_per_launch=1):
         self._v = ctypes.c_void_p()
         self.params = params if isinstance(params, Params) else Params.from_dict(params)
         self.w, self.h, self.depth, self.channels = int(w), int(h), int(depth), int(channels)
-        _check(lib().dis_video_create(ctypes.byref(self.params), self.channels, self.w, self.h, int(device),
-                                      self.depth, ctypes.byref(self._v)), None)
+        # pairs_per_launch > 1 (dividing depth): batched handles, one launch chain per that many pushes
+        _check(lib().dis_video_create_batched(ctypes.byref(self.params), self.channels, self.w, self.h, int(device),
+                                              self.depth, int(pairs_per_launch), ctypes.byref(self._v)), None)
         shape = (self.h, self.w) if self.channels == 1 else (self.h, self.w, self.channels)
         self._frames = [pinned_empty(shape, np.uint8) for _ in range(self.depth + 1)]
         if output not in ("level", "full"):

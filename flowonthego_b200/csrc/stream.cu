@@ -10,6 +10,11 @@
 // (pair k-1); pair k, on the next handle, waits for that upload through an event.  So a pair costs one u8
 // frame of H2D traffic instead of two, and up to `depth` pairs overlap their copies and kernels.
 //
+// Batched mode (dis_video_create_batched, pairs_per_launch = nb > 1): depth / nb batched handles (dis_create_batch);
+// the pairs of nb consecutive pushes are collected and go out as ONE launch chain, so a pair costs 1/nb of the
+// launches (the device-resident rate of bench.py instead of the single-pair one) at the price of up to nb - 1 frame
+// times of latency; a pop of a pair whose batch is still collecting submits the partial batch.
+//
 // Pyramid reuse ("frame k+1's pyramid is reused as the next pair's first image"): with depth >= 2
 // the handles are chained (engine_chain): pair k builds only the pyramid of its second frame (with gradients) and
 // reads its first frame's pyramid from the workspace of the handle that ran pair k-1, once that handle's pyramid
@@ -26,15 +31,23 @@
 
 struct dis_video {
   int w = 0, h = 0, noc = 1, device = 0, depth = 0;
+  int nb = 1;                               // pairs per kernel launch (batched handles), depth = eng.size() * nb
   size_t frame_bytes = 0, flow_floats = 0;  // flow_floats: full-resolution field
   int out_mode = DIS_VIDEO_OUT_LEVEL;
   int lw = 0, lh = 0;                       // size of the level-lv_l flow (the engine's own output)
   std::vector<dis_handle*> eng;
   std::vector<uint8_t*> d_frame;       // ring, depth + 2 slots
   std::vector<cudaEvent_t> uploaded;   // per slot: upload finished
-  std::vector<float*> d_flow;          // per handle
+  std::vector<float*> d_flow;          // per pair in flight (handle * nb + position in its batch)
   std::vector<cudaEvent_t> done;       // per handle: D2H finished
-  std::vector<float*> host_out;        // per handle: destination of the pair in flight
+  std::vector<float*> host_out;        // per pair in flight: destination
+  // batched handles: the pairs of a handle's next launch, collected push by push
+  std::vector<std::vector<const uint8_t*>> bat_a, bat_b;
+  std::vector<int> fill;               // per handle: pairs collected and not yet submitted
+  std::vector<long long> first_pair;   // per handle: index of the first pair of its current / latest batch
+  std::vector<long long> last_pair;    // per handle: index of the last pair of its latest batch (-1: never used)
+  std::vector<int> pair_handle;        // per pair in flight: the handle it went to
+  int cur = 0;                         // the handle that is collecting (handles are used round-robin)
   long long pushed = 0;                // frames pushed so far
   long long popped = 0;                // pairs handed back so far
   bool chained = false;                // engine_chain done (workspaces hold the second frame's gradients)
@@ -52,13 +65,63 @@ namespace {
     }                                                                                                        \
   } while (0)
 
+// Launches the pairs collected on handle k (one pair when nb = 1) and queues their copies to the host.
+int submit_batch(dis_video* v, int k) {
+  const int n = v->fill[k], nH = (int)v->eng.size(), nslots = v->depth + 2;
+  const long long p0 = v->first_pair[k];
+  cudaStream_t st = static_cast<cudaStream_t>(dis_stream(v->eng[k]));
+  const size_t rowb = (size_t)v->w * v->noc;
+  const bool reuse = v->reuse && p0 >= 1;  // (nb = 1 only) pair - 1 built this pair's first frame as its second one
+  if (reuse) {
+    // its pyramid (and with it the upload) is ready when the previous handle's pyramid event fires ...
+    CUV(cudaStreamWaitEvent(st, dis::engine_pyramid_event(v->eng[(k + nH - 1) % nH]), 0));
+    // ... and this handle's own second-frame pyramid, about to be overwritten, was the first frame of the pair that
+    // ran on the next handle depth-1 pairs ago
+    if (p0 >= v->depth) CUV(cudaStreamWaitEvent(st, v->done[(k + 1) % nH], 0));
+  } else {
+    // the first image of the first pair was uploaded on the previous handle's stream (the other frames on this one)
+    CUV(cudaStreamWaitEvent(st, v->uploaded[p0 % nslots], 0));
+  }
+  int rc;
+  if (v->nb == 1) {
+    dis::engine_set_reuse(v->eng[k], reuse);
+    rc = dis_submit_u8_device(v->eng[k], v->bat_a[k][0], v->bat_b[k][0], v->w, v->h, (int)rowb, v->d_flow[k]);
+  } else {
+    rc = dis_submit_u8_device_batch(v->eng[k], n, v->bat_a[k].data(), v->bat_b[k].data(), v->w, v->h, (int)rowb,
+                                    &v->d_flow[(size_t)k * v->nb]);
+  }
+  if (rc != DIS_OK) {
+    dis::set_global_error("%s", dis_last_error(v->eng[k]));
+    return rc;
+  }
+  for (int j = 0; j < n; ++j) {
+    float* dst = v->host_out[(p0 + j) % v->depth];
+    if (v->out_mode == DIS_VIDEO_OUT_LEVEL) {  // the engine's own output, straight from the handle's workspace
+      CUV(cudaMemcpyAsync(dst, dis_level_flow_ptr(v->eng[k], j), (size_t)v->lw * v->lh * 2 * sizeof(float),
+                          cudaMemcpyDeviceToHost, st));
+    } else {
+      CUV(cudaMemcpyAsync(dst, v->d_flow[(size_t)k * v->nb + j], v->flow_floats * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+  }
+  CUV(cudaEventRecord(v->done[k], st));
+  v->fill[k] = 0;
+  v->cur = (k + 1) % nH;  // the next pair starts a batch on the next handle
+  return DIS_OK;
+}
+
 }  // namespace
 
 extern "C" {
 
 int dis_video_create(const dis_params* params, int channels, int w, int h, int device, int depth, dis_video** out) {
-  if (!params || !out || w <= 0 || h <= 0 || depth < 1 || depth > 256) {
-    dis::set_global_error("dis_video_create: bad argument");
+  return dis_video_create_batched(params, channels, w, h, device, depth, 1, out);
+}
+
+int dis_video_create_batched(const dis_params* params, int channels, int w, int h, int device, int depth,
+                             int pairs_per_launch, dis_video** out) {
+  const int nb = pairs_per_launch;
+  if (!params || !out || w <= 0 || h <= 0 || depth < 1 || depth > 256 || nb < 1 || nb > 8 || depth % nb != 0) {
+    dis::set_global_error("dis_video_create: bad argument (depth 1 ... 256, pairs_per_launch 1 ... 8 dividing depth)");
     return DIS_ERR_INVALID_ARG;
   }
   *out = nullptr;
@@ -68,23 +131,30 @@ int dis_video_create(const dis_params* params, int channels, int w, int h, int d
   v->noc = channels;
   v->device = device;
   v->depth = depth;
+  v->nb = nb;
   v->frame_bytes = (size_t)w * h * channels;
   v->flow_floats = (size_t)w * h * 2;
   auto bail = [&](int rc) {
     dis_video_destroy(v);
     return rc;
   };
-  for (int i = 0; i < depth; ++i) {
+  for (int i = 0; i < depth / nb; ++i) {
     dis_handle* e = nullptr;
-    const int rc = dis_create_c(params, channels, w, h, device, &e);
+    const int rc = nb > 1 ? dis_create_batch(params, channels, w, h, device, nb, &e) : dis_create_c(params, channels, w, h, device, &e);
     if (rc != DIS_OK) return bail(rc);
     v->eng.push_back(e);
+    v->bat_a.emplace_back(nb, nullptr);
+    v->bat_b.emplace_back(nb, nullptr);
+    v->fill.push_back(0);
+    v->first_pair.push_back(0);
+    v->last_pair.push_back(-1);
   }
+  v->pair_handle.assign(depth, 0);
   dis_level_flow_size(v->eng[0], &v->lw, &v->lh);
   // Pyramid reuse is on by default for shallow pipelines (live streams, where it shortens a pair's critical path) and
   // off for deep ones: measured on the C5 stream at depth 64, the dependency between consecutive pairs costs more
   // (6 980 pairs/s) than the saved pyramid work brings (7 180 without).  dis_video_set_reuse() overrides.
-  if (depth >= 2 && depth <= 8) {
+  if (nb == 1 && depth >= 2 && depth <= 8) {
     const int rc = dis_video_set_reuse(v, 1);
     if (rc != DIS_OK) return bail(rc);
   }
@@ -99,13 +169,14 @@ int dis_video_create(const dis_params* params, int channels, int w, int h, int d
   }
   for (int i = 0; i < depth; ++i) {
     float* p = nullptr;
-    cudaEvent_t ev = nullptr;
-    if (cudaMalloc(&p, v->flow_floats * sizeof(float)) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess)
-      return bail(DIS_ERR_CUDA);
+    if (cudaMalloc(&p, v->flow_floats * sizeof(float)) != cudaSuccess) return bail(DIS_ERR_CUDA);
     v->d_flow.push_back(p);
-    v->done.push_back(ev);
     v->host_out.push_back(nullptr);
+  }
+  for (int i = 0; i < depth / nb; ++i) {
+    cudaEvent_t ev = nullptr;
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return bail(DIS_ERR_CUDA);
+    v->done.push_back(ev);
   }
   *out = v;
   return DIS_OK;
@@ -130,8 +201,8 @@ int dis_video_set_reuse(dis_video* v, int on) {
     dis::set_global_error("dis_video_set_reuse: only before the first frame is pushed");
     return DIS_ERR_INVALID_ARG;
   }
-  if (on && v->depth < 2) {
-    dis::set_global_error("dis_video_set_reuse: needs depth >= 2");
+  if (on && (v->depth < 2 || v->nb > 1)) {
+    dis::set_global_error("dis_video_set_reuse: needs depth >= 2 and one pair per launch");
     return DIS_ERR_INVALID_ARG;
   }
   if (on && !v->chained) {  // pair k reads its first frame's pyramid from the handle of pair k-1
@@ -167,7 +238,9 @@ size_t dis_video_flow_size(const dis_video* v, int* w_out, int* h_out) {
   return lvl ? (size_t)v->lw * v->lh * 2 : v->flow_floats;
 }
 
-dis_handle* dis_video_handle(dis_video* v, int k) { return (v && k >= 0 && k < v->depth) ? v->eng[k] : nullptr; }
+dis_handle* dis_video_handle(dis_video* v, int k) { return (v && k >= 0 && k < (int)v->eng.size()) ? v->eng[k] : nullptr; }
+
+int dis_video_handles(const dis_video* v) { return v ? (int)v->eng.size() : 0; }
 
 int dis_video_pending(const dis_video* v) { return v ? (int)((v->pushed > 0 ? v->pushed - 1 : 0) - v->popped) : 0; }
 
@@ -177,15 +250,20 @@ int dis_video_pop(dis_video* v, float** flow_out) {
     dis::set_global_error("dis_video_pop: no pair in flight");
     return DIS_ERR_INVALID_ARG;
   }
-  const int k = (int)(v->popped % v->depth);
+  const int k = v->pair_handle[v->popped % v->depth];
   CUV(cudaSetDevice(v->device));
+  if (v->fill[k] > 0 && v->first_pair[k] <= v->popped) {  // its batch is still collecting: send what there is
+    const int rc = submit_batch(v, k);
+    if (rc != DIS_OK) return rc;
+  }
   const int rc = dis_wait(v->eng[k]);  // the handle's stream carries the graph and the copy-out
   if (rc != DIS_OK) {
     dis::set_global_error("%s", dis_last_error(v->eng[k]));
     return rc;
   }
-  if (flow_out) *flow_out = v->host_out[k];
-  v->host_out[k] = nullptr;
+  const int slot = (int)(v->popped % v->depth);
+  if (flow_out) *flow_out = v->host_out[slot];
+  v->host_out[slot] = nullptr;
   ++v->popped;
   return DIS_OK;
 }
@@ -207,9 +285,16 @@ int dis_video_push(dis_video* v, const uint8_t* frame, int pitch, float* flow_ou
   CUV(cudaSetDevice(v->device));
   const int nslots = v->depth + 2;
   const int slot = (int)(f % nslots);
-  // the pair that carries this frame's upload: pair f-1 (this frame is its second image); the very first frame
-  // rides on handle 0's stream
-  const int k = (int)((f > 0 ? f - 1 : 0) % v->depth);
+  // the handle that carries this frame's upload: that of pair f-1 (this frame is its second image); the very first
+  // frame rides on handle 0's stream
+  const long long pair = f > 0 ? f - 1 : 0;
+  const int k = v->cur;  // the collecting handle
+  if (f > 0 && v->fill[k] == 0 && v->last_pair[k] >= 0 && v->first_pair[k] >= v->popped) {
+    // the handle's latest batch was never waited for (the pop of its first pair does that for the whole batch); only
+    // possible after pops forced partial batches out
+    dis::set_global_error("dis_video_push: all %d handles hold pairs in flight, pop one first", (int)v->eng.size());
+    return DIS_ERR_INVALID_ARG;
+  }
   cudaStream_t st = static_cast<cudaStream_t>(dis_stream(v->eng[k]));
   // slot reuse: its previous tenant, frame f - nslots, was last read by pair f - nslots, which was popped
   // before pair f - 1 could be admitted (pending < depth) -- nothing to wait for
@@ -219,32 +304,15 @@ int dis_video_push(dis_video* v, const uint8_t* frame, int pitch, float* flow_ou
   ++v->pushed;
   if (f == 0) return DIS_OK;
   const int prev = (int)((f - 1) % nslots);
-  const long long pair = f - 1;
-  const bool reuse = v->reuse && pair >= 1;  // pair - 1 built this pair's first frame as its second one
-  if (reuse) {
-    // its pyramid (and with it the upload) is ready when the previous handle's pyramid event fires ...
-    CUV(cudaStreamWaitEvent(st, dis::engine_pyramid_event(v->eng[(k + v->depth - 1) % v->depth]), 0));
-    // ... and this handle's own second-frame pyramid, about to be overwritten, was the first frame of the pair that
-    // ran on the next handle depth-1 pairs ago
-    if (pair >= v->depth) CUV(cudaStreamWaitEvent(st, v->done[(k + 1) % v->depth], 0));
-  } else {
-    CUV(cudaStreamWaitEvent(st, v->uploaded[prev], 0));  // first image was uploaded on the previous pair's stream
-  }
-  dis::engine_set_reuse(v->eng[k], reuse);
-  const int rc = dis_submit_u8_device(v->eng[k], v->d_frame[prev], v->d_frame[slot], v->w, v->h, (int)rowb, v->d_flow[k]);
-  if (rc != DIS_OK) {
-    dis::set_global_error("%s", dis_last_error(v->eng[k]));
-    return rc;
-  }
-  if (v->out_mode == DIS_VIDEO_OUT_LEVEL) {  // the engine's own output, straight from the handle's workspace
-    CUV(cudaMemcpyAsync(flow_out, dis_level_flow_ptr(v->eng[k], 0), (size_t)v->lw * v->lh * 2 * sizeof(float),
-                        cudaMemcpyDeviceToHost, st));
-  } else {
-    CUV(cudaMemcpyAsync(flow_out, v->d_flow[k], v->flow_floats * sizeof(float), cudaMemcpyDeviceToHost, st));
-  }
-  CUV(cudaEventRecord(v->done[k], st));
-  v->host_out[k] = flow_out;
-  return DIS_OK;
+  const int j = v->fill[k];  // position in the handle's batch
+  if (j == 0) v->first_pair[k] = pair;
+  v->last_pair[k] = pair;
+  v->bat_a[k][j] = v->d_frame[prev];
+  v->bat_b[k][j] = v->d_frame[slot];
+  v->host_out[pair % v->depth] = flow_out;
+  v->pair_handle[pair % v->depth] = k;
+  v->fill[k] = j + 1;
+  return v->fill[k] == v->nb ? submit_batch(v, k) : DIS_OK;
 }
 
 }  // extern "C"

@@ -228,6 +228,14 @@ int dis_submit_u8_device_batch(dis_handle* h, int n_pairs, const uint8_t* const*
  * popped.  Not thread-safe per object. */
 typedef struct dis_video dis_video;
 int dis_video_create(const dis_params* params, int channels, int w, int h, int device, int depth, dis_video** out);
+/* Throughput variant: the pairs of `pairs_per_launch` (1 ... 8, dividing depth) consecutive pushes go out as ONE
+ * launch chain on a batched handle (dis_create_batch), depth / pairs_per_launch handles in all.  Same results bit
+ * for bit, 1 / pairs_per_launch of the kernel launches per pair; a pair's flow is ready only after the last frame
+ * of its batch was pushed (dis_video_pop submits a partial batch rather than wait for frames that may never come;
+ * a partial batch still occupies its handle, so after such pops dis_video_push can ask for another pop before
+ * `depth` pairs are in flight).  No pyramid reuse in this mode. */
+int dis_video_create_batched(const dis_params* params, int channels, int w, int h, int device, int depth,
+                             int pairs_per_launch, dis_video** out);
 void dis_video_destroy(dis_video* v);
 /* What dis_video_push copies back per pair.  DIS_VIDEO_OUT_LEVEL (the default for streams): the engine's own
  * output as OFC::OFClass delivers it -- level lv_l, dis_video_flow_size() floats, 1.04 MB per 1080p pair at
@@ -244,8 +252,10 @@ int dis_video_set_reuse(dis_video* v, int on);
 int dis_video_reuse(const dis_video* v);
 /* Floats per flow field handed back in the current output mode, and its width / height. */
 size_t dis_video_flow_size(const dis_video* v, int* w_out, int* h_out);
-/* k-th engine handle (0 <= k < depth) -- e.g. for dis_stream(); owned by the video object. */
+/* k-th engine handle (0 <= k < dis_video_handles() = depth / pairs_per_launch) -- e.g. for dis_stream(); owned by
+ * the video object. */
 dis_handle* dis_video_handle(dis_video* v, int k);
+int dis_video_handles(const dis_video* v);
 int dis_video_push(dis_video* v, const uint8_t* frame, int pitch, float* flow_out);
 int dis_video_pop(dis_video* v, float** flow_out);
 int dis_video_pending(const dis_video* v);

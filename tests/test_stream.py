@@ -53,6 +53,45 @@ def test_stream_equals_pairwise(channels, depth, reuse):
         F.FlowStream(p, w, h, depth=1, reuse=True)
 
 
+@pytest.mark.parametrize("channels,depth,nb,output", [(1, 8, 4, "level"), (1, 6, 3, "full"), (3, 4, 2, "level"), (1, 8, 8, "level")])
+def test_batched_stream_equals_pairwise(channels, depth, nb, output):
+    """dis_video_create_batched: the pairs of nb pushes go out as one launch chain; every flow still equals a separate
+    run on its pair, including the partial batches a pop forces out and the tail of the sequence."""
+    w, h, n = 322, 198, 14
+    frames = sequence(w, h, n, channels=channels)
+    p = F.Params.preset(2, 1024, verbosity=0).copy(lv_f=3, lv_l=1)
+    with F.FlowStream(p, w, h, depth=depth, channels=channels, output=output, pairs_per_launch=nb) as s:
+        assert not s.reuse
+        flows = list(s.flows(frames))
+        # a second pass on the same object, popping early: partial batches
+        s2 = []
+        for k, fr in enumerate(frames[:6]):
+            s.push(fr)
+            if k in (2, 3):
+                s2.append(s.pop().copy())
+        while s.pending:
+            s2.append(s.pop().copy())
+    assert len(flows) == n - 1
+    with F.Engine(p, w, h, channels=channels) as e:
+        for k in range(n - 1):
+            full = e.run_u8(frames[k], frames[k + 1])
+            ref = full if output == "full" else e.level_flow(w, h)
+            assert bits_differ(flows[k], ref) == 0, k
+        # second pass: its first pair is (last frame of the first pass, frames[0]), then frames[0..5]
+        full = e.run_u8(frames[-1], frames[0])
+        ref = [full if output == "full" else e.level_flow(w, h)]
+        for k in range(5):
+            full = e.run_u8(frames[k], frames[k + 1])
+            ref.append(full.copy() if output == "full" else e.level_flow(w, h))
+        assert len(s2) == len(ref)
+        for k in range(len(ref)):
+            assert bits_differ(s2[k], ref[k]) == 0, ("second pass", k)
+    with pytest.raises(F.DisError):
+        F.FlowStream(p, w, h, depth=6, pairs_per_launch=4)   # must divide depth
+    with pytest.raises(F.DisError):
+        F.FlowStream(p, w, h, depth=8, pairs_per_launch=4, reuse=True)
+
+
 def test_stream_protocol_errors():
     p = F.Params.preset(2, 1024, verbosity=0).copy(lv_f=2, lv_l=1)
     fr = sequence(128, 96, 4)
