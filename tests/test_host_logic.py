@@ -194,3 +194,28 @@ def test_native_jpeg_decode_matches_opencv(tmp_path):
         path = os.path.join(ref, "images", n + ".jpg")
         if os.path.exists(path):
             assert np.array_equal(F.read_image_gray(path), cv2.imread(path, cv2.IMREAD_GRAYSCALE)), n
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` runs without a GPU and without the product library, and prints the one JSON line the
+    driver reads: the metric / unit / config of the B200 arm, `impl`, a `cpu_baseline` that describes this very run and
+    an `e2e` object with zero copy bytes (the round-1 arm timed process start-up instead of the engine)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "frame_pairs_per_sec" and d["unit"] == "pairs/s"
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["steps"] == 1 and d["warmup"] == 0
+    assert d["config"]["config_id"] == "c5" and d["config"]["resolution"] == [1920, 1080]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] > 0
+    # steady state: the pool's rate agrees with cores / single-thread time (not with process start-up)
+    assert 0.3 < cb["agreement"] < 1.5, cb
+    assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "libdis_b200" not in r.stderr  # never loads the product
