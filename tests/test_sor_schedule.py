@@ -136,3 +136,29 @@ def test_small_level_schedule_is_the_lexicographic_sweep(w, h, T, C):
         got = scheduled(A, B, du0, T, omega, C)
     assert not np.isnan(got).any(), "a pixel was never written by the last sweep"
     assert (got.view(np.uint32) != ref.view(np.uint32)).sum() == 0
+
+
+def wavefront_tickets(T, K):
+    """Ticket -> (sweep t, row block k) as k_sor_wavefront decodes it: items ordered by key = 2 t + k, sweeps ascending
+    inside a key (varref.cu, 'decode ticket')."""
+    order = []
+    for key in range(2 * (T - 1) + K):
+        for t in range(T):
+            k = key - 2 * t
+            if 0 <= k < K:
+                order.append((t, k))
+    return order
+
+
+@pytest.mark.parametrize("T,K", [(1, 1), (3, 1), (3, 9), (1, 68), (5, 4), (40, 5), (256, 2)])
+def test_wavefront_tickets_respect_the_dependencies(T, K):
+    """Persistent warps take tickets in this order and only after finishing their item, so the launch cannot deadlock
+    for ANY number of CTAs iff every item an item waits for -- the block above in the same sweep, the same block and
+    the block below in the previous sweep -- holds a smaller ticket."""
+    order = wavefront_tickets(T, K)
+    assert len(order) == T * K and len(set(order)) == T * K
+    ticket = {it: n for n, it in enumerate(order)}
+    for (t, k), n in ticket.items():
+        for dep in ((t, k - 1), (t - 1, k), (t - 1, k + 1)):
+            if dep in ticket:
+                assert ticket[dep] < n, ((t, k), dep)
